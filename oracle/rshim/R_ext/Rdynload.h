@@ -1,0 +1,1 @@
+/* oracle R shim: intentionally empty (see R.h) */
