@@ -1,0 +1,214 @@
+// common.cuh -- shared device-side definitions for the batched EBEN fit kernels (sm_100a).
+//
+// Execution model: ONE thread block runs ONE complete EBEN fit (one (fold, alpha, lambda)
+// point of R/CrossValidate.R's grid) from initialisation to hold-out error, entirely on the
+// device; a grid of persistent blocks (a multiple of the 148 SMs) pulls fits from an atomic
+// queue ordered by expected cost.  All blocks share the per-fold training matrices, which are
+// small enough to stay resident in the 126 MB L2, so the score contractions stream them from
+// L2 rather than HBM.  Per-fit state (active-set inverse, candidate cache, statistics) lives
+// in a per-block slab of global memory plus shared memory for the hot vectors.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace pareben {
+
+enum : int { ACT_REEST = 0, ACT_ADD = 1, ACT_DEL = -1, ACT_TERM = 10, ACT_NONE = -10 };
+
+// status bits, mirrored in include/pareben.h
+enum : int { ST_CAP = 1, ST_NOT_PD = 2, ST_NONFINITE = 4, ST_ITER_MAX = 8 };
+
+// Constants that differ between the four reference translation units.
+struct Variant {
+    int epis;
+    int binomial;
+    double n_add;            // block threshold factor
+    double ml_delta;         // minimum worthwhile delta-ML
+    double reest_tol;        // |dlog alpha| below which a lone re-estimate terminates
+    double init_alpha_max;
+    double init_alpha_min;
+};
+
+struct FoldData {
+    const double *Xtr;       // [ntr][K] row-major training rows
+    const double *ytr;       // [ntr]
+    const double *Xte;       // [nte][K] row-major held-out rows
+    const double *yte;       // [nte]
+    const double *scale;     // [Kc] column norms of the training rows (1 where the column is all zero)
+    int ntr, nte;
+};
+
+struct Problem {
+    int N, K, Kc, n_folds, epis, prior;
+    int cap;                 // basis cap actually used (<= the reference's basisMax)
+    int nmax;                // max ntr over folds
+    const FoldData *folds;   // [n_folds + 1]; index 0 = all rows, f = rows with fold_id != f
+};
+
+struct FitTask { int fold; double alpha, lambda; int out_index; };
+
+struct FitOutputs {
+    double *fold_err;        // [n] indexed by out_index
+    int *status, *n_selected, *n_iter;
+    // optional full-model dump for pareben_fit (batch of 1)
+    int *m_out; int *used_out; double *beta_out; double *var_out; double *scalars_out; // wald, intercept0, intercept1, extra
+    double *flops;           // single accumulator (atomicAdd)
+};
+
+// Per-block slab carved out of one big allocation.
+struct Slab {
+    double *sigma, *sigma_new, *H;      // cap*cap each
+    double *phi;                        // nmax * cap, column-major (column j at phi + j*N)
+    double *G;                          // cap * Kc: physical rows, row r at G + r*Kc
+    double *xt, *S_in, *Q_in, *S_out, *Q_out, *dml, *aroot;   // Kc each
+    double *t, *e, *phinew, *w1, *w2;   // nmax each
+    double *mu, *alpha, *gamma, *tmp, *u, *colk;  // cap (+1) each
+    int *used, *grow;                   // cap
+    int *unused, *upos, *amap, *action, *block;   // Kc each
+};
+
+__host__ __device__ inline size_t slab_doubles(int cap, int nmax, int Kc)
+{
+    return (size_t)3 * cap * cap + (size_t)nmax * cap + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
+           (size_t)6 * (cap + 1);
+}
+__host__ __device__ inline size_t slab_ints(int cap, int Kc) { return (size_t)2 * cap + (size_t)5 * Kc; }
+__host__ __device__ inline size_t slab_bytes(int cap, int nmax, int Kc)
+{
+    size_t b = slab_doubles(cap, nmax, Kc) * 8 + slab_ints(cap, Kc) * 4;
+    return (b + 255) & ~(size_t)255;
+}
+
+__device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
+{
+    Slab s;
+    double *d = reinterpret_cast<double *>(base);
+    s.sigma = d; d += (size_t)cap * cap;
+    s.sigma_new = d; d += (size_t)cap * cap;
+    s.H = d; d += (size_t)cap * cap;
+    s.phi = d; d += (size_t)nmax * cap;
+    s.G = d; d += (size_t)cap * Kc;
+    s.xt = d; d += Kc; s.S_in = d; d += Kc; s.Q_in = d; d += Kc; s.S_out = d; d += Kc; s.Q_out = d; d += Kc;
+    s.dml = d; d += Kc; s.aroot = d; d += Kc;
+    s.t = d; d += nmax; s.e = d; d += nmax; s.phinew = d; d += nmax; s.w1 = d; d += nmax; s.w2 = d; d += nmax;
+    s.mu = d; d += cap + 1; s.alpha = d; d += cap + 1; s.gamma = d; d += cap + 1;
+    s.tmp = d; d += cap + 1; s.u = d; d += cap + 1; s.colk = d; d += cap + 1;
+    int *i = reinterpret_cast<int *>(d);
+    s.used = i; i += cap; s.grow = i; i += cap;
+    s.unused = i; i += Kc; s.upos = i; i += Kc; s.amap = i; i += Kc; s.action = i; i += Kc; s.block = i; i += Kc;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// block-level primitives.  `red` is a shared scratch of >= 33 doubles, `redi` >= 33 ints.
+struct Scratch { double *red; int *redi; };
+
+__device__ inline double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ inline double block_sum(double v, const Scratch &sc)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();                       // protect scratch from the previous use
+    if (lane == 0) sc.red[wid] = v;
+    __syncthreads();
+    double tot = 0;
+    for (int w = 0; w < nw; w++) tot += sc.red[w];   // same order in every thread -> identical result
+    return tot;
+}
+
+__device__ inline void block_sum2(double &a, double &b, const Scratch &sc)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    a = warp_sum(a); b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { sc.red[wid] = a; sc.red[32 + wid] = b; }
+    __syncthreads();
+    double ta = 0, tb = 0;
+    for (int w = 0; w < nw; w++) { ta += sc.red[w]; tb += sc.red[32 + w]; }
+    a = ta; b = tb;
+}
+
+// argmax of (val, key): largest val, ties -> smallest key.  Only val > 0 competes (the reference's
+// scans start from 0 with a strict '>').  Returns arg (0 when nothing is positive) and the max.
+__device__ inline void block_argmax(double val, int key, int arg, const Scratch &sc, double &best, int &best_arg)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double v2 = __shfl_xor_sync(0xffffffffu, val, o);
+        int k2 = __shfl_xor_sync(0xffffffffu, key, o);
+        int a2 = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (v2 > val || (v2 == val && k2 < key)) { val = v2; key = k2; arg = a2; }
+    }
+    __syncthreads();
+    if (lane == 0) { sc.red[wid] = val; sc.redi[wid] = key; sc.redi[32 + wid] = arg; }
+    __syncthreads();
+    double bv = 0; int bk = 0x7fffffff, ba = 0;
+    for (int w = 0; w < nw; w++) {
+        double v2 = sc.red[w]; int k2 = sc.redi[w], a2 = sc.redi[32 + w];
+        if (v2 > bv || (v2 == bv && v2 > 0 && k2 < bk)) { bv = v2; bk = k2; ba = a2; }
+    }
+    best = bv; best_arg = ba;
+}
+
+// Ordered compaction: list[] receives, in ascending order, every c in [0,n) with pred(c);
+// pos[c] (optional) receives its position.  Values stored are c + store_offset.
+template <class Pred>
+__device__ inline int block_compact(int n, Pred pred, int *list, int *pos, int store_offset, const Scratch &sc)
+{
+    const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    int base = 0;
+    for (int c0 = 0; c0 < n; c0 += T) {
+        const int c = c0 + threadIdx.x;
+        const bool f = c < n && pred(c);
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        __syncthreads();
+        if (lane == 0) sc.redi[wid] = __popc(m);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int w = 0; w < nw; w++) { int v = sc.redi[w]; if (w < wid) off += v; tot += v; }
+        if (f) {
+            int p = base + off + __popc(m & ((1u << lane) - 1u));
+            list[p] = c + store_offset;
+            if (pos) pos[c] = p;
+        }
+        base += tot;
+    }
+    __syncthreads();
+    return base;
+}
+
+// Candidate id -> loci.  Main effects: (c, c).  Pairs are enumerated i<j row-major after the K
+// main effects (NeFull2.c:115-134): c = K + i*(2K-i-1)/2 + (j-i-1).
+__device__ inline void decode_candidate(int c, int K, int &i, int &j)
+{
+    if (c < K) { i = j = c; return; }
+    long long p = (long long)c - K;
+    double kk = 2.0 * K - 1.0;
+    long long ii = (long long)floor((kk - sqrt(kk * kk - 8.0 * (double)p)) * 0.5);
+    if (ii < 0) ii = 0;
+    while (ii > 0 && ii * (2LL * K - ii - 1) / 2 > p) ii--;
+    while ((ii + 1) * (2LL * K - (ii + 1) - 1) / 2 <= p) ii++;
+    i = (int)ii;
+    j = (int)(p - ii * (2LL * K - ii - 1) / 2) + i + 1;
+}
+
+template <bool EPIS>
+struct Cand {
+    int i, j;
+    __device__ inline Cand(int c, int K) { if (EPIS) decode_candidate(c, K, i, j); else i = j = c; }
+    __device__ inline double at(const double *Xrow) const
+    {
+        if (EPIS) return i == j ? Xrow[i] : Xrow[i] * Xrow[j];
+        return Xrow[i];
+    }
+};
+
+}  // namespace pareben

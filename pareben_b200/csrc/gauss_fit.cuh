@@ -1,0 +1,647 @@
+// gauss_fit.cuh -- one Gaussian EBEN fit per thread block (main-effect and Epis variants).
+//
+// Device re-design of the reference's Gaussian solver; behaviour follows
+//   /root/reference/EBEN_orig/src/elasticNetLinearNeMainEff.c (entry :55-242, inner solver
+//   :248-809, init :976-1108, CacheBP :1144-1201, FullStat :1209-1341, DeltaML :1372-1582,
+//   ActionAdd :1585-1723, ActionDel :1725-1822, FinalUpdate :1841-1921)
+//   and elasticNetLinearNeFull2.c for Epis (same skeleton, constants per SURVEY.md App. A),
+// followed by the hold-out score of /root/reference/R/GetModelError.R:6-32.
+// Differences in kind, not in result: the N x N matrix C_inv (:742-781) is never formed (only
+// 1'C^-1 1 and 1'C^-1 y are needed, :172-188); the SPD inverse is an in-block symmetric sweep
+// instead of dpotrf/dpotri; the candidate cache is stored as physical rows + a permutation;
+// pair columns for Epis are generated on the fly from two loci and never stored.
+#pragma once
+#include "common.cuh"
+
+namespace pareben {
+
+struct GaussState {
+    int M, n_unused;
+    double beta;
+    int status;
+    double flops;
+};
+
+// ---- contraction: out(r, c) = sum_h x_c[h] * V_r[h]  for r in [0,R), c in [0,Kc) -------------
+// Thread-per-candidate, RC right-hand sides per pass kept in registers; the V tile is staged in
+// shared memory ([TH rows][RC]) so every X element fetched from L2 feeds RC FMAs.
+// Summation over rows is sequential in h for every (r, c): identical arithmetic for identical
+// columns, so exact duplicates tie exactly.
+constexpr int RC = 8;     // right-hand sides per register tile
+constexpr int TH = 64;    // rows per shared-memory tile
+
+template <bool EPIS, class ColPtr, class Store>
+__device__ inline void contract(const double *__restrict__ X, int N, int K, int Kc, int R, ColPtr colptr,
+                                Store store, double *sV /* TH*RC doubles */)
+{
+    const int T = blockDim.x;
+    for (int c0 = 0; c0 < Kc; c0 += T) {
+        const int c = c0 + threadIdx.x;
+        const bool live = c < Kc;
+        Cand<EPIS> cd(live ? c : 0, K);
+        for (int r0 = 0; r0 < R; r0 += RC) {
+            const int nr = min(RC, R - r0);
+            double acc[RC];
+#pragma unroll
+            for (int r = 0; r < RC; r++) acc[r] = 0.0;
+            for (int h0 = 0; h0 < N; h0 += TH) {
+                const int nh = min(TH, N - h0);
+                __syncthreads();
+                for (int idx = threadIdx.x; idx < TH * RC; idx += T) {
+                    const int r = idx / TH, h = idx - r * TH;      // consecutive threads -> consecutive rows (coalesced)
+                    double v = 0.0;
+                    if (r < nr && h < nh) v = colptr(r0 + r)[h0 + h];
+                    sV[h * RC + r] = v;
+                }
+                __syncthreads();
+                if (live) {
+                    const double *xr = X + (size_t)h0 * K;
+                    for (int h = 0; h < nh; h++, xr += K) {
+                        const double x = cd.at(xr);
+                        const double4 *v4 = reinterpret_cast<const double4 *>(sV + h * RC);
+                        const double4 a = v4[0], b = v4[1];
+                        acc[0] = fma(x, a.x, acc[0]); acc[1] = fma(x, a.y, acc[1]);
+                        acc[2] = fma(x, a.z, acc[2]); acc[3] = fma(x, a.w, acc[3]);
+                        acc[4] = fma(x, b.x, acc[4]); acc[5] = fma(x, b.y, acc[5]);
+                        acc[6] = fma(x, b.z, acc[6]); acc[7] = fma(x, b.w, acc[7]);
+                    }
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int r = 0; r < RC; r++) if (r < nr) store(r0 + r, c, acc[r]);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// dot products of active columns with a vector: out[i] = sum_h phi_i[h] * v[h], one warp per i.
+__device__ inline void phi_dot(const double *phi, int N, int M, const double *v, double *out, double scale)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = wid; i < M; i += nw) {
+        const double *p = phi + (size_t)i * N;
+        double z = 0;
+        for (int h = lane; h < N; h += 32) z = fma(p[h], v[h], z);
+        z = warp_sum(z);
+        if (lane == 0) out[i] = z * scale;
+    }
+    __syncthreads();
+}
+
+// In-place inverse of a symmetric positive-definite M x M matrix (leading dimension M) by the
+// symmetric sweep operator.  Plays the role of dpotrf + dpotri (MainEff.c:1346-1369).  Returns
+// false (to every thread) when a pivot is not positive.
+__device__ inline bool spd_inverse_sweep(double *a, int M, double *colk, const Scratch &sc)
+{
+    const int T = blockDim.x;
+    bool ok = true;
+    for (int k = 0; k < M; k++) {
+        const double d = a[k * M + k];
+        if (!(d > 0.0)) { ok = false; break; }        // uniform: every thread reads the same value
+        for (int i = threadIdx.x; i < M; i += T) colk[i] = a[k * M + i];
+        __syncthreads();
+        const double dinv = 1.0 / d;
+        for (int idx = threadIdx.x; idx < M * M; idx += T) {
+            const int j = idx / M, i = idx - j * M;
+            double v;
+            if (i == k && j == k) v = -dinv;
+            else if (i == k) v = colk[j] * dinv;
+            else if (j == k) v = colk[i] * dinv;
+            else v = a[idx] - (colk[i] * colk[j]) * dinv;
+            a[idx] = v;
+        }
+        __syncthreads();
+    }
+    if (ok) {
+        for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -a[idx];
+    }
+    __syncthreads();
+    return ok;
+}
+
+__device__ inline void refresh_out(const Slab &s, int M, int Kc)
+{   // S_out/Q_out = S_in/Q_in, with the in-model correction (MainEff.c:664-671, 1320-1338)
+    for (int c = threadIdx.x; c < Kc; c += blockDim.x) {
+        double si = s.S_in[c], qi = s.Q_in[c];
+        const int i = s.amap[c];
+        if (i >= 0) {
+            const double a = s.alpha[i];
+            const double den = a - si;
+            qi = a * qi / den;
+            si = a * si / den;
+        }
+        s.S_out[c] = si; s.Q_out[c] = qi;
+    }
+    __syncthreads();
+}
+
+__device__ inline double block_var(const double *t, int N, const Scratch &sc)
+{   // varTargets (MainEff.c:1826-1838)
+    double m = 0;
+    for (int h = threadIdx.x; h < N; h += blockDim.x) m += t[h];
+    m = block_sum(m, sc) / N;
+    double v = 0;
+    for (int h = threadIdx.x; h < N; h += blockDim.x) { double d = t[h] - m; v = fma(d, d, v); }
+    return block_sum(v, sc) / (N - 1);
+}
+
+__device__ inline void posterior_mean(Slab &s, GaussState &g, int N)
+{   // Mu = beta * SIGMA * PHI' t   (MainEff.c:1256-1280)
+    phi_dot(s.phi, N, g.M, s.t, s.tmp, 1.0);
+    const int M = g.M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        double z = 0;
+        for (int j = 0; j < M; j++) z = fma(s.sigma[j * M + i], s.tmp[j], z);
+        s.mu[i] = z * g.beta;
+    }
+    __syncthreads();
+}
+
+__device__ inline void full_stat(Slab &s, GaussState &g, int N, int Kc, bool first, const Scratch &sc)
+{   // fEBLinearFullStat* (MainEff.c:1209-1341)
+    const int M = g.M;
+    if (first) {                                                    // :1236-1246
+        double h = 0;
+        for (int k = threadIdx.x; k < N; k += blockDim.x) h = fma(s.phi[k], s.phi[k], h);
+        h = block_sum(h, sc);
+        if (threadIdx.x == 0) { s.H[0] = h * g.beta + s.alpha[0]; s.sigma[0] = 1.0 / s.H[0]; }
+        __syncthreads();
+    }
+    posterior_mean(s, g, N);
+    for (int i = 1 + threadIdx.x; i < M; i += blockDim.x) s.gamma[i] = 1.0 - s.sigma[i * M + i] * s.alpha[i];
+    const double beta = g.beta;
+    for (int c = threadIdx.x; c < Kc; c += blockDim.x) {
+        double quad = 0, gm = 0;
+        for (int j = 0; j < M; j++) {
+            const double *sj = s.sigma + j * M;
+            double z = 0;
+            for (int p = 0; p < M; p++) z = fma(s.G[(size_t)s.grow[p] * Kc + c], sj[p], z);
+            const double gj = s.G[(size_t)s.grow[j] * Kc + c];
+            quad = fma(z, gj, quad);
+            gm = fma(gj, s.mu[j], gm);
+        }
+        s.S_in[c] = beta - beta * quad * beta;
+        s.Q_in[c] = beta * (s.xt[c] - gm);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) g.flops += (double)Kc * (2.0 * M * M + 2.0 * M);
+    refresh_out(s, M, Kc);
+}
+
+__device__ inline bool final_update(Slab &s, GaussState &g, int N, const Scratch &sc)
+{   // FinalUpdate*: H = beta PHI'PHI + diag(alpha), SIGMA = H^-1, Mu  (MainEff.c:1841-1921)
+    const int M = g.M;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int npair = M * (M + 1) / 2;
+    for (int p = wid; p < npair; p += nw) {
+        // p -> (i <= j) by rows of the upper triangle
+        int j = (int)floor((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+        while ((j + 1) * (j + 2) / 2 <= p) j++;
+        while (j * (j + 1) / 2 > p) j--;
+        const int i = p - j * (j + 1) / 2;
+        const double *a = s.phi + (size_t)i * N, *b = s.phi + (size_t)j * N;
+        double z = 0;
+        for (int h = lane; h < N; h += 32) z = fma(a[h], b[h], z);
+        z = warp_sum(z);
+        if (lane == 0) {
+            double v = z * g.beta;
+            if (i == j) v += s.alpha[i];
+            s.H[j * M + i] = v; s.H[i * M + j] = v;
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) s.sigma[idx] = s.H[idx];
+    __syncthreads();
+    const bool ok = spd_inverse_sweep(s.sigma, M, s.colk, sc);
+    posterior_mean(s, g, N);
+    return ok;
+}
+
+struct Decision { double best; int nu; int any_delete; };
+
+template <bool EPIS>
+__device__ inline Decision delta_ml(Slab &s, GaussState &g, const Variant &v, int N, int Kc, double lambda,
+                                    double alpha_en, double residual, double var_y, int iter, int i_iter,
+                                    const Scratch &sc)
+{   // fEBDeltaML* (MainEff.c:1372-1582; NeFull2.c:1227-1404)
+    const double l1 = lambda * alpha_en, l2 = lambda * (1 - alpha_en);
+    const int M = g.M;
+    int prio_add = 0, prio_del = 0;
+    if (M < 10) { prio_add = 1; prio_del = 0; }
+    if (M > 100 || (!EPIS && M >= N) || residual <= var_y * 0.1) { prio_add = 0; prio_del = 1; }
+    double lbest = 0; int lkey = 0x7fffffff, larg = 0;
+    int f_add = 0, f_del = 0;
+    for (int c = threadIdx.x; c < Kc; c += blockDim.x) {
+        const int i = s.amap[c];
+        const double so = s.S_out[c], qo = s.Q_out[c];
+        double d_ml = 0; int act = ACT_NONE;
+        const double a = so - qo * qo + 2 * l1 + l2;
+        const double b = (so + l2) * (so + 4 * l1 + l2);
+        const double gm = 2 * l1 * (so + l2) * (so + l2);
+        const double dl = b * b - 4 * a * gm;
+        if (a < 0 && dl > 0) {
+            const double r = (-b - sqrt(dl)) / (2 * a);
+            const double L = (log(r / (r + so + l2)) + qo * qo / (r + so + l2)) * 0.5 - l1 / r;
+            if (L > 0) {
+                s.aroot[c] = r + l2;
+                if (i >= 0) {
+                    act = ACT_REEST;
+                    const double o = s.alpha[i] - l2;
+                    d_ml = 0.5 * (log(r * (o + so + l2) / (o * (r + so + l2))) +
+                                  qo * qo * (1 / (r + so + l2) - 1 / (o + so + l2))) -
+                           l1 * (1 / r - 1 / o);
+                } else {
+                    act = ACT_ADD;
+                    d_ml = L;
+                    if (!EPIS) f_add = 1;          // only the main-effect file ever sets anyToAdd (:1484)
+                }
+            }
+        } else if (i >= 0 && M > 1) {
+            f_del = 1;
+            act = ACT_DEL;
+            const double o = s.alpha[i] - l2;
+            const double L = (log(o / (o + so + l2)) + qo * qo / (o + so + l2)) * 0.5 - l1 / o;
+            d_ml = -L;
+        }
+        s.dml[c] = d_ml; s.action[c] = act;
+        const int key = i >= 0 ? i : M + s.upos[c];    // visiting order of the reference's two scans
+        if (d_ml > lbest || (d_ml == lbest && d_ml > 0 && key < lkey)) { lbest = d_ml; lkey = key; larg = c; }
+    }
+    const int any_add = __syncthreads_or(f_add);
+    const int any_del = __syncthreads_or(f_del);
+    Decision out;
+    out.any_delete = any_del;
+    bool rescan = false;
+    if ((any_add && prio_add) || (any_del && prio_del)) {        // :1527-1556
+        for (int c = threadIdx.x; c < Kc; c += blockDim.x) {
+            const int act = s.action[c];
+            if (act == ACT_REEST) s.dml[c] = 0;
+            else if (act == ACT_DEL) { if (any_add && prio_add && !prio_del) s.dml[c] = 0; }
+            else if (act == ACT_ADD) { if (any_del && prio_del && !prio_add) s.dml[c] = 0; }
+        }
+        rescan = true;
+    }
+    if (!EPIS && ((!any_add && iter == 1 && i_iter < 10) || (!any_add && residual >= var_y * 0.95))) {   // :1557-1577
+        for (int c = threadIdx.x; c < Kc; c += blockDim.x) if (s.action[c] == ACT_DEL) s.dml[c] = 0;
+        rescan = true;
+    }
+    if (rescan) {       // rescans run in ascending candidate order
+        lbest = 0; lkey = 0x7fffffff; larg = 0;
+        for (int c = threadIdx.x; c < Kc; c += blockDim.x) {
+            const double d = s.dml[c];
+            if (d > lbest) { lbest = d; lkey = c; larg = c; }
+        }
+    }
+    block_argmax(lbest, lkey, larg, sc, out.best, out.nu);
+    return out;
+}
+
+// One complete Gaussian fit.  Every thread of the block executes this with identical scalars.
+template <bool EPIS>
+__device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v, Slab &s, double lambda,
+                          double alpha_en, const FitTask &task, const FitOutputs &out, double *sV,
+                          const Scratch &sc)
+{
+    const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x;
+    const double *X = F.Xtr, *y = F.ytr, *scale = F.scale;
+    GaussState g; g.M = 1; g.n_unused = 0; g.beta = 0; g.status = 0; g.flops = 0;
+
+    for (int j = threadIdx.x; j < cap; j += T) { s.grow[j] = j; s.alpha[j] = 0; s.mu[j] = 0; }
+    double b = 0;
+    for (int h = threadIdx.x; h < N; h += T) b += y[h];
+    b = block_sum(b, sc) / N;
+    const double var_y = block_var(y, N, sc);
+    const double eps = var_y * 0.01;
+    double residvar = 1e10, vk = 1e-30, vk0, err = 1000;
+    int iter = 0;
+
+    while (iter < 100 && err > 1e-8 && residvar >= eps) {          // MainEff.c:155-197
+        iter++;
+        vk0 = vk;
+        for (int h = threadIdx.x; h < N; h += T) s.t[h] = y[h] - b;
+        __syncthreads();
+        // ---------------- inner solver (LinearFastEmpBayes*, MainEff.c:248-809) ----------------
+        int ini_removed = 1;
+        if (iter <= 1) {                                             // initialisation, :1003-1090
+            ini_removed = 0;
+            g.M = 1;
+            if (threadIdx.x == 0) s.used[0] = 1;
+            const double isc = 1 / scale[0];
+            for (int h = threadIdx.x; h < N; h += T) s.phi[h] = X[(size_t)h * K] * isc;
+            __syncthreads();
+            const double var = block_var(s.t, N, sc);
+            if (!EPIS) g.beta = 1 / (var * 0.01 + 1e-10);
+            else { double sd = sqrt(var); if (sd < 1e-6) sd = 1e-6; g.beta = 1 / ((sd * 0.1) * (sd * 0.1)); }
+            double p = 0, q = 0;
+            for (int h = threadIdx.x; h < N; h += T) { p = fma(s.phi[h], s.phi[h], p); q = fma(s.phi[h], s.t[h], q); }
+            block_sum2(p, q, sc);
+            p *= g.beta; q *= g.beta;
+            double a = p * p / (q * q - p);
+            if (a < 0) a = v.init_alpha_max;
+            if (a > v.init_alpha_max) a = v.init_alpha_max;
+            if (threadIdx.x == 0) s.alpha[0] = a;
+        }
+        __syncthreads();
+        // Used -> amap; Unused rebuilt in ascending order (:1092-1107)
+        for (int c = threadIdx.x; c < Kc; c += T) s.amap[c] = -1;
+        for (int j = threadIdx.x; j < cap; j += T) s.gamma[j] = 0;       // gamma is Calloc'ed per call (:344)
+        __syncthreads();
+        for (int j = threadIdx.x; j < g.M; j += T) s.amap[s.used[j] - 1] = j;
+        __syncthreads();
+        g.n_unused = block_compact(Kc, [&](int c) { return s.amap[c] < 0; }, s.unused, s.upos, 1, sc);
+        const int initial = s.used[0];
+        // candidate cache G = PHI'X/s and xt = X't/s  (CacheBP*, :1144-1201)
+        {
+            const int M = g.M;
+            contract<EPIS>(X, N, K, Kc, M + 1,
+                [&](int r) -> const double * { return r < M ? s.phi + (size_t)r * N : s.t; },
+                [&](int r, int c, double acc) {
+                    if (r < M) s.G[(size_t)s.grow[r] * Kc + c] = acc / scale[c];
+                    else s.xt[c] = acc / scale[c];
+                }, sV);
+            if (threadIdx.x == 0) g.flops += 2.0 * N * (double)Kc * (M + 1);
+        }
+        int i_iter = 0;
+        full_stat(s, g, N, Kc, iter == 1, sc);
+        int selected = ACT_NONE, last = 0, n_update = 0, jj = -1;
+        const int it_max = iter == 1 ? 10 : 100;
+        while (!last) {
+            i_iter++;
+            Decision d = delta_ml<EPIS>(s, g, v, N, Kc, lambda, alpha_en, residvar, var_y, iter, i_iter, sc);
+            int nu = d.nu, worthwhile;
+            if (selected == ACT_TERM && !ini_removed && g.M > 1) nu = -1;          // :426-430
+            if (nu == -1 && ini_removed) { worthwhile = 0; selected = ACT_TERM; }
+            else if (nu == -1 && !ini_removed && g.M > 1) {                        // :437-446
+                worthwhile = 1; nu = initial - 1;
+                __syncthreads();
+                if (threadIdx.x == 0) { s.action[nu] = ACT_DEL; s.block[0] = nu; }
+                __syncthreads();
+                n_update = 1; ini_removed = 1; selected = ACT_DEL;
+            } else {
+                worthwhile = 1;
+                const int best_is_add = s.action[nu] == ACT_ADD;
+                double cutoff = d.best * (best_is_add ? v.n_add : 1.0);
+                if (cutoff < v.ml_delta) cutoff = v.ml_delta;
+                const int best_is_del = s.action[nu] == ACT_DEL;
+                n_update = block_compact(Kc, [&](int c) { return s.dml[c] >= cutoff; }, s.block, nullptr, 0, sc);
+                if (best_is_del && n_update > 1) n_update = 1;                     // :474
+                if (n_update == 0) worthwhile = 0;
+            }
+            if (!worthwhile) selected = ACT_TERM;
+            if (worthwhile) {
+                for (int iu = 0; iu < n_update; iu++) {
+                    __syncthreads();
+                    nu = s.block[iu];
+                    selected = s.action[nu];
+                    const double new_alpha = s.aroot[nu];
+                    if (selected == ACT_REEST || selected == ACT_DEL) {
+                        // The reference searches Used for nu and silently keeps the previous jj when the
+                        // search fails (forced removal of an initial basis that a regular delete already
+                        // took out, :498-509).  Keep that, but never index outside the active set.
+                        const int a = s.amap[nu];
+                        if (a >= 0) jj = a;
+                        if (jj < 0 || jj >= g.M) { g.status |= ST_NOT_PD; selected = ACT_TERM; }
+                    }
+                    if (selected == ACT_REEST && fabs(log(new_alpha) - log(s.alpha[jj])) <= v.reest_tol && !d.any_delete)
+                        selected = ACT_TERM;                                       // :541-549
+                    const int M = g.M;
+                    bool updated = false;
+                    if (selected == ACT_REEST) {                                   // :553-596
+                        const double old = s.alpha[jj];
+                        const double kappa = 1.0 / (s.sigma[jj * M + jj] + 1.0 / (new_alpha - old));
+                        const double mujj = s.mu[jj];
+                        const double *sj = s.sigma + jj * M;
+                        __syncthreads();
+                        if (threadIdx.x == 0) s.alpha[jj] = new_alpha;
+                        for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mujj * kappa * sj[i];
+                        for (int idx = threadIdx.x; idx < M * M; idx += T) {
+                            const int j = idx / M, i = idx - j * M;
+                            s.sigma_new[idx] = s.sigma[idx] - kappa * sj[i] * sj[j];
+                        }
+                        const double beta = g.beta;
+                        for (int c = threadIdx.x; c < Kc; c += T) {
+                            double z = 0;
+                            for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sj[j], z);
+                            const double bz = beta * z;
+                            s.S_in[c] += bz * bz * kappa;
+                            s.Q_in[c] += beta * mujj * kappa * z;
+                        }
+                        if (threadIdx.x == 0) g.flops += 2.0 * Kc * (double)M;
+                        updated = true;
+                    } else if (selected == ACT_ADD) {                              // ActionAdd*, :1585-1723
+                        if (M + 1 > cap) { g.status |= ST_CAP; selected = ACT_TERM; }
+                        else {
+                            // new normalised column (on the fly for pairs)
+                            {
+                                Cand<EPIS> cd(nu, K);
+                                const double isc = 1 / scale[nu];
+                                for (int h = threadIdx.x; h < N; h += T) s.phinew[h] = cd.at(X + (size_t)h * K) * isc;
+                            }
+                            __syncthreads();
+                            const int grow_new = s.grow[M];
+                            contract<EPIS>(X, N, K, Kc, 1,
+                                [&](int) -> const double * { return s.phinew; },
+                                [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, sV);
+                            phi_dot(s.phi, N, M, s.phinew, s.tmp, g.beta);             // tmp = beta PHI' phi
+                            for (int i = threadIdx.x; i < M; i += T) {
+                                double z = 0;
+                                for (int j = 0; j < M; j++) z = fma(s.sigma[i * M + j], s.tmp[j], z);
+                                s.u[i] = z;
+                            }
+                            for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)M * N + h] = s.phinew[h];
+                            const double s_ii = 1.0 / (new_alpha + s.S_in[nu]);
+                            const double mu_i = s_ii * s.Q_in[nu];
+                            __syncthreads();
+                            if (threadIdx.x == 0) { s.alpha[M] = new_alpha; }
+                            for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mu_i * s.u[i];
+                            if (threadIdx.x == 0) s.mu[M] = mu_i;
+                            const int M1 = M + 1;
+                            for (int idx = threadIdx.x; idx < M1 * M1; idx += T) {
+                                const int j = idx / M1, i = idx - j * M1;
+                                double val;
+                                if (i < M && j < M) val = s.sigma[j * M + i] + (s_ii * s.u[i]) * s.u[j];
+                                else if (i == M && j == M) val = s_ii;
+                                else val = -s_ii * s.u[i < M ? i : j];
+                                s.sigma_new[idx] = val;
+                            }
+                            const double beta = g.beta;
+                            for (int c = threadIdx.x; c < Kc; c += T) {
+                                double z = 0;
+                                for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], s.u[j], z);
+                                const double mci = beta * s.G[(size_t)grow_new * Kc + c] - beta * z;
+                                s.S_in[c] -= mci * mci * s_ii;
+                                s.Q_in[c] -= mu_i * mci;
+                            }
+                            __syncthreads();
+                            if (threadIdx.x == 0) {
+                                s.used[M] = nu + 1;
+                                s.amap[nu] = M;
+                                const int p = s.upos[nu], nun = g.n_unused - 1;   // Unused: swap-with-last (:621-625)
+                                if (p < nun) { const int lastc = s.unused[nun] - 1; s.unused[p] = lastc + 1; s.upos[lastc] = p; }
+                                g.flops += 2.0 * N * (double)Kc + 2.0 * Kc * (double)M;
+                            }
+                            g.n_unused--;
+                            g.M = M + 1;
+                            updated = true;
+                        }
+                    } else if (selected == ACT_DEL) {                              // ActionDel*, :1725-1822
+                        const int lastj = M - 1;
+                        const int mujj = (int)s.mu[jj];                            // `int Mujj` truncation (:1746-1747)
+                        const double *sj = s.sigma + jj * M;
+                        const double sjj = sj[jj];
+                        const double al_last = s.alpha[lastj];
+                        __syncthreads();
+                        for (int i = threadIdx.x; i < M; i += T) {
+                            double m = s.mu[i] - mujj * sj[i] / sjj;
+                            s.mu[i] = m;
+                        }
+                        for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)jj * N + h] = s.phi[(size_t)lastj * N + h];
+                        // Schur downdate, then move the last row/column into slot jj (:1754-1776)
+                        for (int idx = threadIdx.x; idx < lastj * lastj; idx += T) {
+                            const int j = idx / lastj, i = idx - j * lastj;
+                            const int si = (i == jj) ? lastj : i, sjx = (j == jj) ? lastj : j;
+                            s.sigma_new[idx] = s.sigma[sjx * M + si] - sj[si] / sjj * sj[sjx];
+                        }
+                        const double beta = g.beta;
+                        for (int c = threadIdx.x; c < Kc; c += T) {
+                            double z = 0;
+                            for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sj[j], z);
+                            const double bz = beta * z;
+                            s.S_in[c] += bz * bz / sjj;
+                            s.Q_in[c] += beta * z * mujj / sjj;
+                        }
+                        __syncthreads();
+                        if (threadIdx.x == 0) {
+                            s.alpha[jj] = al_last;
+                            // mu[jj] must be the *updated* last entry
+                            s.mu[jj] = s.mu[lastj];
+                            const int gr = s.grow[jj]; s.grow[jj] = s.grow[lastj]; s.grow[lastj] = gr;
+                            const int moved = s.used[lastj];
+                            s.used[jj] = moved;
+                            s.amap[nu] = -1;
+                            if (jj != lastj) s.amap[moved - 1] = jj;
+                            s.unused[g.n_unused] = nu + 1; s.upos[nu] = g.n_unused;
+                            g.flops += 2.0 * Kc * (double)M;
+                        }
+                        g.n_unused++;
+                        g.M = M - 1;
+                        updated = true;
+                    }
+                    __syncthreads();
+                    if (updated) {                                                 // :657-681
+                        double *tmpp = s.sigma; s.sigma = s.sigma_new; s.sigma_new = tmpp;
+                        refresh_out(s, g.M, Kc);
+                        const int Mn = g.M;
+                        for (int i = threadIdx.x; i < Mn; i += T) s.gamma[i] = 1 - s.alpha[i] * s.sigma[i * Mn + i];
+                        __syncthreads();
+                    }
+                }
+            }
+            if (selected == ACT_TERM || i_iter <= 10 || i_iter % 5 == 0 || n_update >= 2) {      // :685-729
+                const int M = g.M;
+                double ee = 0;
+                for (int h = threadIdx.x; h < N; h += T) {
+                    double pm = 0;
+                    for (int j = 0; j < M; j++) pm = fma(s.phi[(size_t)j * N + h], s.mu[j], pm);
+                    const double e = s.t[h] - pm;
+                    ee = fma(e, e, ee);
+                }
+                ee = block_sum(ee, sc);
+                double sg = 0;
+                for (int i = 0; i < M; i++) sg += s.gamma[i];
+                const double beta_old = g.beta;
+                g.beta = (N - sg) / ee;
+                const double vt = block_var(s.t, N, sc);
+                if (g.beta > 1e6 / vt) g.beta = 1e6 / vt;
+                if (fabs(log(g.beta) - log(beta_old)) > 1e-6) {
+                    if (!final_update(s, g, N, sc)) g.status |= ST_NOT_PD;
+                    if (selected != ACT_TERM) full_stat(s, g, N, Kc, false, sc);
+                }
+            }
+            if (selected == ACT_TERM && ini_removed) last = 1;
+            if ((i_iter == it_max && g.M == 1) || i_iter > it_max) last = 1;
+            if (i_iter == it_max) selected = ACT_TERM;
+        }
+        // ---------------- intercept update: b = 1'C^-1 y / (1'C^-1 1 [+1e-10]) ----------------
+        {
+            const int M = g.M;
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+            for (int j = wid; j < M; j += nw) {
+                const double *p = s.phi + (size_t)j * N;
+                double a1 = 0, ay = 0;
+                for (int h = lane; h < N; h += 32) { a1 += p[h]; ay = fma(p[h], y[h], ay); }
+                a1 = warp_sum(a1); ay = warp_sum(ay);
+                if (lane == 0) { s.tmp[j] = a1; s.u[j] = ay; }
+            }
+            __syncthreads();
+            double q11 = 0, q1y = 0, sy = 0;
+            for (int j = threadIdx.x; j < M; j += T) {
+                double z = 0;
+                for (int k = 0; k < M; k++) z = fma(s.sigma[j * M + k], s.tmp[k], z);
+                q11 = fma(z, s.tmp[j], q11); q1y = fma(z, s.u[j], q1y);
+            }
+            block_sum2(q11, q1y, sc);
+            for (int h = threadIdx.x; h < N; h += T) sy += y[h];
+            sy = block_sum(sy, sc);
+            const double cinv = g.beta * N - g.beta * g.beta * q11;
+            const double cinvy = g.beta * sy - g.beta * g.beta * q1y;
+            b = EPIS ? cinvy / cinv : cinvy / (cinv + 1e-10);                      // MainEff.c:188 vs NeFull2.c:202
+            vk = 0;
+            for (int i = 0; i < M; i++) vk += s.alpha[i];
+            err = fabs(vk - vk0) / M;
+            residvar = 1 / (g.beta + 1e-10);
+        }
+    }
+    if (iter >= 100) g.status |= ST_ITER_MAX;
+
+    // ---------------- hold-out score (R/GetModelError.R:6-32) ----------------
+    const int M = g.M;
+    __syncthreads();
+    for (int i = threadIdx.x; i < M; i += T) s.tmp[i] = s.mu[i] / scale[s.used[i] - 1];   // Beta[,3] (:221)
+    __syncthreads();
+    double sse = 0;
+    for (int h = threadIdx.x; h < F.nte; h += T) {
+        const double *xr = F.Xte + (size_t)h * K;
+        double pred = 0;
+        for (int i = 0; i < M; i++) {
+            const double w = s.tmp[i];
+            if (w != 0) { Cand<EPIS> cd(s.used[i] - 1, K); pred = fma(cd.at(xr), w, pred); }
+        }
+        const double r = F.yte[h] - (b + pred);
+        sse = fma(r, r, sse);
+    }
+    sse = block_sum(sse, sc);
+    int nsel = 0;
+    for (int i = 0; i < M; i++) nsel += s.tmp[i] != 0;
+    if (!isfinite(sse)) g.status |= ST_NONFINITE;
+    if (threadIdx.x == 0) {
+        const int o = task.out_index;
+        if (out.fold_err) out.fold_err[o] = sse;
+        if (out.status) out.status[o] = g.status;
+        if (out.n_selected) out.n_selected[o] = nsel;
+        if (out.n_iter) out.n_iter[o] = iter;
+        if (out.flops) atomicAdd(out.flops, g.flops);
+        if (out.m_out) {          // full-model dump (pareben_fit)
+            out.m_out[0] = M;
+            double wd = 0;        // Wald score mu'H mu with H read at leading dimension M (:206-215)
+            for (int i = 0; i < M; i++) {
+                double z = 0;
+                for (int j = 0; j < M; j++) z += s.mu[j] * s.H[i * M + j];
+                wd += z * s.mu[i];
+            }
+            for (int i = 0; i < M; i++) {
+                const int c = s.used[i] - 1;
+                out.used_out[i] = s.used[i];
+                out.beta_out[i] = s.mu[i] / scale[c];
+                out.var_out[i] = s.sigma[i * M + i] / (scale[c] * scale[c]);
+            }
+            out.scalars_out[0] = wd; out.scalars_out[1] = b; out.scalars_out[2] = 0;
+            out.scalars_out[3] = 1 / (g.beta + 1e-10);
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace pareben

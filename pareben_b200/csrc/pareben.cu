@@ -1,0 +1,605 @@
+// pareben.cu -- host side of libpareben.so: problem upload, per-fold layout kernels, the
+// persistent batched-fit launch, and the extern "C" entry points declared in include/pareben.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false --shared ...
+// (-fmad=false keeps the scalar decision formulas un-contracted like the reference's x86 build;
+//  the hot loops use explicit fma()).
+#include "../../include/pareben.h"
+#include "common.cuh"
+#include "gauss_fit.cuh"
+#include "binom_fit.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pareben;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            char buf_[512];                                                                       \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw std::make_pair((int)(e_ == cudaErrorMemoryAllocation ? PAREBEN_ENOMEM : PAREBEN_ECUDA), std::string(buf_)); \
+        }                                                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// layout kernels
+// Xout[r][k] = Xcol[k*N + rows[r]]  (column-major in, row-major compacted out), 32x32 tiles
+__global__ void gather_rows_kernel(const double *__restrict__ Xcol, int N, int K, const int *__restrict__ rows,
+                                   int nrows, double *__restrict__ Xout)
+{
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int kk = threadIdx.y; kk < 32; kk += blockDim.y) {
+        const int r = r0 + threadIdx.x, k = k0 + kk;
+        if (r < nrows && k < K) tile[kk][threadIdx.x] = Xcol[(size_t)k * N + rows[r]];
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int r = r0 + rr, k = k0 + threadIdx.x;
+        if (r < nrows && k < K) Xout[(size_t)r * K + k] = tile[threadIdx.x][rr];
+    }
+}
+
+__global__ void gather_vec_kernel(const double *__restrict__ y, const int *__restrict__ rows, int nrows,
+                                  double *__restrict__ out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nrows) out[r] = y[rows[r]];
+}
+
+// scale[c] = sqrt(sum_h x_c[h]^2), 1 when the column is all zero (MainEff.c:87-99, NeFull2.c:100-135)
+template <bool EPIS>
+__global__ void scales_kernel(const double *__restrict__ X, int N, int K, int Kc, double *__restrict__ scale)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Kc) return;
+    Cand<EPIS> cd(c, K);
+    double z = 0;
+    for (int h = 0; h < N; h++) { const double x = cd.at(X + (size_t)h * K); z = fma(x, x, z); }
+    if (z == 0) z = 1;
+    scale[c] = sqrt(z);
+}
+
+// lambda_max pieces (R/BuildGrid.R:5-32): max over candidates of x_c' r / ||x_c||
+template <bool EPIS>
+__global__ void lambda_max_kernel(const double *__restrict__ X, int N, int K, int c_begin, int c_end,
+                                  const double *__restrict__ resp, double *__restrict__ block_max)
+{
+    __shared__ double red[32];
+    const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    double v = -1e300;
+    if (c < c_end) {
+        Cand<EPIS> cd(c, K);
+        double z = 0, nn = 0;
+        for (int h = 0; h < N; h++) { const double x = cd.at(X + (size_t)h * K); z = fma(x, resp[h], z); nn = fma(x, x, nn); }
+        if (nn > 0) v = z / sqrt(nn);
+    }
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = red[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmax(m, red[w]);
+        block_max[blockIdx.x] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the persistent batched-fit kernel: one block = one fit at a time, fits pulled from a queue
+constexpr int FIT_THREADS = 256;
+
+template <bool EPIS, bool BINOMIAL>
+__global__ void __launch_bounds__(FIT_THREADS)
+eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_tasks, int *queue, char *slabs,
+                size_t slab_stride, FitOutputs out)
+{
+    __shared__ __align__(32) double sV[TH * RC];
+    __shared__ double red[66];
+    __shared__ int redi[66];
+    __shared__ int s_task;
+    Scratch sc{red, redi};
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_task = atomicAdd(queue, 1);
+        __syncthreads();
+        const int ti = s_task;
+        if (ti >= n_tasks) break;
+        const FitTask task = tasks[ti];
+        const FoldData F = P.folds[task.fold];
+        Slab s = carve_slab(slabs + (size_t)blockIdx.x * slab_stride, P.cap, P.nmax, P.Kc);
+        if (BINOMIAL) binom_fit<EPIS>(P, F, v, s, task.lambda, task.alpha, task, out, sV, sc);
+        else gauss_fit<EPIS>(P, F, v, s, task.lambda, task.alpha, task, out, sV, sc);
+    }
+}
+
+// FP64 FMA peak probe: 8 independent chains per thread.
+__global__ void dfma_peak_kernel(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// FP64 tensor-core probe: mma.sync.m8n8k4.f64 chains (DMMA), 4 independent accumulator pairs.
+__global__ void dmma_peak_kernel(double *out, int iters)
+{
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0000001;
+    double c0 = 0, c1 = 0, d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+    for (int i = 0; i < iters; i++) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(e0), "+d"(e1) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(f0), "+d"(f1) : "d"(a), "d"(b));
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = c0 + c1 + d0 + d1 + e0 + e1 + f0 + f1;
+}
+
+Variant make_variant(int epis, int prior)
+{   // SURVEY.md Appendix A, "variant constant table"
+    Variant v;
+    v.epis = epis; v.binomial = prior == PAREBEN_BINOMIAL;
+    if (!v.binomial) {
+        if (!epis) { v.n_add = 0.9;  v.ml_delta = 1e-3; v.reest_tol = 1e-3; v.init_alpha_max = 1e2; v.init_alpha_min = 0; }
+        else       { v.n_add = 0.99; v.ml_delta = 1e-2; v.reest_tol = 0.1;  v.init_alpha_max = 1e3; v.init_alpha_min = 0; }
+    } else {
+        if (!epis) { v.n_add = 0.90; v.ml_delta = 1e-3; v.reest_tol = 1e-3; v.init_alpha_max = 1e3; v.init_alpha_min = 1e-3; }
+        else       { v.n_add = 0.99; v.ml_delta = 1e-3; v.reest_tol = 1e-3; v.init_alpha_max = 1e3; v.init_alpha_min = 1e-3; }
+    }
+    return v;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct pareben_problem {
+    int device = 0;
+    int n = 0, k = 0, kc = 0, n_folds = 0, epis = 0, prior = 0, cap = 0, nmax = 0;
+    int sm_count = 0;
+    std::vector<void *> allocs;          // everything cudaMalloc'ed for this problem
+    FoldData *d_folds = nullptr;
+    std::vector<FoldData> h_folds;
+    double *d_Xcol = nullptr, *d_y = nullptr;     // full data, column-major (kept for lambda_max)
+    char *d_slabs = nullptr; size_t slab_stride = 0; int n_slabs = 0;
+    int *d_queue = nullptr;
+    double *d_flops = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_flops = 0, last_ms = 0; int last_launches = 0;
+
+    template <class T> T *dalloc(size_t n)
+    {
+        void *p = nullptr;
+        CU(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        allocs.push_back(p);
+        return static_cast<T *>(p);
+    }
+    ~pareben_problem()
+    {
+        cudaSetDevice(device);
+        for (void *p : allocs) cudaFree(p);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static int reference_basis_max(int n_train, int k, int kc, int epis, int prior)
+{
+    if (prior == PAREBEN_BINOMIAL) return epis ? 2 * k : k;                        // bMax (EBelasticNet.Binomial.R:8,30)
+    if (!epis) { int b = (int)(1e7 / kc); return b > kc ? kc : b; }                // MainEff.c:68-69
+    return n_train > k ? 2 * k : (n_train < 200 ? 4 * k : k);                      // NeFull2.c:67-80
+}
+
+extern "C" int pareben_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" const char *pareben_last_error(void) { return g_err.c_str(); }
+extern "C" int pareben_version(void) { return PAREBEN_VERSION; }
+
+extern "C" int pareben_problem_create(pareben_problem **out, int device, const double *basis, int n, int k,
+                                      const double *target, const int *fold_id, int n_folds, int epis, int prior)
+{
+    if (!out || !basis || !target || n < 2 || k < 1 || n_folds < 0 || (n_folds > 0 && !fold_id))
+        return fail(PAREBEN_EINVAL, "pareben_problem_create: bad argument");
+    if (prior != PAREBEN_GAUSSIAN && prior != PAREBEN_BINOMIAL) return fail(PAREBEN_EINVAL, "prior must be 0 or 1");
+    if (epis && (long long)k * (k + 1) / 2 > 0x7fffffffLL) return fail(PAREBEN_EINVAL, "k(k+1)/2 exceeds int32");
+    if (pareben_device_count() <= device || device < 0) return fail(PAREBEN_ENODEVICE, "no usable CUDA device");
+    pareben_problem *p = new pareben_problem();
+    try {
+        p->device = device;
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        p->sm_count = prop.multiProcessorCount;
+        p->n = n; p->k = k; p->epis = epis; p->prior = prior; p->n_folds = n_folds;
+        p->kc = epis ? (int)((long long)k * (k + 1) / 2) : k;
+        CU(cudaStreamCreate(&p->stream));
+        CU(cudaEventCreate(&p->ev0)); CU(cudaEventCreate(&p->ev1));
+
+        p->d_Xcol = p->dalloc<double>((size_t)n * k);
+        p->d_y = p->dalloc<double>(n);
+        CU(cudaMemcpyAsync(p->d_Xcol, basis, sizeof(double) * n * k, cudaMemcpyHostToDevice, p->stream));
+        CU(cudaMemcpyAsync(p->d_y, target, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
+
+        // row lists per fold: index 0 = all rows (only materialised when n_folds == 0)
+        const int nf = n_folds;
+        p->h_folds.assign(nf + 1, FoldData{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0});
+        int min_ntr = n;
+        for (int f = (nf == 0 ? 0 : 1); f <= nf; f++) {
+            std::vector<int> tr, te;
+            for (int r = 0; r < n; r++) {
+                if (f == 0) tr.push_back(r);
+                else {
+                    if (fold_id[r] < 1 || fold_id[r] > nf) throw std::make_pair((int)PAREBEN_EINVAL, std::string("fold_id out of range"));
+                    (fold_id[r] != f ? tr : te).push_back(r);
+                }
+            }
+            if (tr.size() < 2) throw std::make_pair((int)PAREBEN_EINVAL, std::string("a fold leaves fewer than 2 training rows"));
+            FoldData &F = p->h_folds[f];
+            F.ntr = (int)tr.size(); F.nte = (int)te.size();
+            p->nmax = std::max(p->nmax, F.ntr);
+            min_ntr = std::min(min_ntr, F.ntr);
+            int *d_rows = p->dalloc<int>(tr.size() + te.size());
+            CU(cudaMemcpyAsync(d_rows, tr.data(), sizeof(int) * tr.size(), cudaMemcpyHostToDevice, p->stream));
+            if (!te.empty())
+                CU(cudaMemcpyAsync(d_rows + tr.size(), te.data(), sizeof(int) * te.size(), cudaMemcpyHostToDevice, p->stream));
+            CU(cudaStreamSynchronize(p->stream));      // tr/te go out of scope
+            double *Xtr = p->dalloc<double>((size_t)F.ntr * k), *ytr = p->dalloc<double>(F.ntr);
+            double *Xte = p->dalloc<double>((size_t)F.nte * k), *yte = p->dalloc<double>(F.nte);
+            double *scale = p->dalloc<double>(p->kc);
+            dim3 blk(32, 8);
+            gather_rows_kernel<<<dim3((F.ntr + 31) / 32, (k + 31) / 32), blk, 0, p->stream>>>(p->d_Xcol, n, k, d_rows, F.ntr, Xtr);
+            gather_vec_kernel<<<(F.ntr + 255) / 256, 256, 0, p->stream>>>(p->d_y, d_rows, F.ntr, ytr);
+            if (F.nte > 0) {
+                gather_rows_kernel<<<dim3((F.nte + 31) / 32, (k + 31) / 32), blk, 0, p->stream>>>(p->d_Xcol, n, k, d_rows + F.ntr, F.nte, Xte);
+                gather_vec_kernel<<<(F.nte + 255) / 256, 256, 0, p->stream>>>(p->d_y, d_rows + F.ntr, F.nte, yte);
+            }
+            if (epis) scales_kernel<true><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
+            else scales_kernel<false><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
+            F.Xtr = Xtr; F.ytr = ytr; F.Xte = Xte; F.yte = yte; F.scale = scale;
+        }
+        CU(cudaGetLastError());
+        p->d_folds = p->dalloc<FoldData>(nf + 1);
+        CU(cudaMemcpyAsync(p->d_folds, p->h_folds.data(), sizeof(FoldData) * (nf + 1), cudaMemcpyHostToDevice, p->stream));
+
+        // basis cap: the reference's basisMax, bounded so that the per-block slab stays reasonable.
+        int cap = reference_basis_max(min_ntr, k, p->kc, epis, prior);
+        const char *env_cap = getenv("PAREBEN_BASIS_CAP");
+        int hard = env_cap ? atoi(env_cap) : 1024;
+        if (hard < 2) hard = 2;
+        if (prior == PAREBEN_BINOMIAL) cap += 1;       // slot 0 is the intercept
+        p->cap = std::min(cap, hard);
+        if (p->cap < 2) p->cap = 2;
+
+        // persistent grid: blocks per SM limited by memory for slabs
+        p->slab_stride = slab_bytes(p->cap, p->nmax, p->kc);
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        int per_sm = 4;
+        const char *env_bps = getenv("PAREBEN_BLOCKS_PER_SM");
+        if (env_bps) per_sm = std::max(1, atoi(env_bps));
+        while (per_sm > 1 && (size_t)per_sm * p->sm_count * p->slab_stride > free_b / 2) per_sm--;
+        p->n_slabs = per_sm * p->sm_count;
+        if ((size_t)p->n_slabs * p->slab_stride > free_b - (free_b >> 3))
+            throw std::make_pair((int)PAREBEN_ENOMEM, std::string("per-block work slabs do not fit in device memory; lower PAREBEN_BASIS_CAP"));
+        p->d_slabs = p->dalloc<char>((size_t)p->n_slabs * p->slab_stride);
+        p->d_queue = p->dalloc<int>(1);
+        p->d_flops = p->dalloc<double>(1);
+        CU(cudaStreamSynchronize(p->stream));
+    } catch (std::pair<int, std::string> &e) {
+        delete p;
+        return fail(e.first, e.second);
+    }
+    *out = p;
+    return PAREBEN_OK;
+}
+
+extern "C" void pareben_problem_destroy(pareben_problem *p) { delete p; }
+
+namespace {
+
+struct DumpBuffers { int *m = nullptr, *used = nullptr; double *beta = nullptr, *var = nullptr, *scalars = nullptr; };
+
+int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double *alpha, const double *lambda,
+                  double *fold_err, int *status, int *n_selected, int *n_iter, DumpBuffers *dump)
+{
+    if (!p || n_fits < 0 || (n_fits > 0 && (!fold || !alpha || !lambda))) return fail(PAREBEN_EINVAL, "pareben_run_fits: bad argument");
+    if (n_fits == 0) return PAREBEN_OK;
+    void *scratch[8] = {nullptr};
+    int ns = 0;
+    try {
+        CU(cudaSetDevice(p->device));
+        std::vector<FitTask> tasks(n_fits);
+        for (int i = 0; i < n_fits; i++) {
+            if (fold[i] < 0 || fold[i] > p->n_folds || (p->n_folds > 0 && fold[i] == 0) || !p->h_folds[fold[i]].Xtr)
+                return fail(PAREBEN_EINVAL, "pareben_run_fits: fold label not available in this problem");
+            tasks[i] = FitTask{fold[i], alpha[i], lambda[i], i};
+        }
+        // expected cost grows as lambda falls (larger active sets): longest fits first
+        std::stable_sort(tasks.begin(), tasks.end(), [](const FitTask &a, const FitTask &b) { return a.lambda < b.lambda; });
+        auto tmp_alloc = [&](size_t bytes) { void *q = nullptr; CU(cudaMalloc(&q, std::max<size_t>(bytes, 8))); scratch[ns++] = q; return q; };
+        FitTask *d_tasks = (FitTask *)tmp_alloc(sizeof(FitTask) * n_fits);
+        double *d_err = (double *)tmp_alloc(sizeof(double) * n_fits);
+        int *d_ints = (int *)tmp_alloc(sizeof(int) * 3 * n_fits);
+        CU(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(FitTask) * n_fits, cudaMemcpyHostToDevice, p->stream));
+        CU(cudaMemsetAsync(p->d_queue, 0, sizeof(int), p->stream));
+        CU(cudaMemsetAsync(p->d_flops, 0, sizeof(double), p->stream));
+        FitOutputs out;
+        out.fold_err = d_err; out.status = d_ints; out.n_selected = d_ints + n_fits; out.n_iter = d_ints + 2 * n_fits;
+        out.m_out = nullptr; out.used_out = nullptr; out.beta_out = nullptr; out.var_out = nullptr; out.scalars_out = nullptr;
+        out.flops = p->d_flops;
+        if (dump) {
+            dump->m = (int *)tmp_alloc(sizeof(int) * (1 + p->cap));
+            dump->used = dump->m + 1;
+            dump->beta = (double *)tmp_alloc(sizeof(double) * (2 * p->cap + 4));
+            dump->var = dump->beta + p->cap; dump->scalars = dump->var + p->cap;
+            out.m_out = dump->m; out.used_out = dump->used; out.beta_out = dump->beta; out.var_out = dump->var; out.scalars_out = dump->scalars;
+        }
+        Problem P;
+        P.N = p->n; P.K = p->k; P.Kc = p->kc; P.n_folds = p->n_folds; P.epis = p->epis; P.prior = p->prior;
+        P.cap = p->cap; P.nmax = p->nmax; P.folds = p->d_folds;
+        const Variant v = make_variant(p->epis, p->prior);
+        const int grid = std::min(p->n_slabs, n_fits);
+        CU(cudaEventRecord(p->ev0, p->stream));
+        if (p->prior == PAREBEN_GAUSSIAN) {
+            if (p->epis) eben_fit_kernel<true, false><<<grid, FIT_THREADS, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
+            else eben_fit_kernel<false, false><<<grid, FIT_THREADS, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
+        } else {
+            if (p->epis) eben_fit_kernel<true, true><<<grid, FIT_THREADS, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
+            else eben_fit_kernel<false, true><<<grid, FIT_THREADS, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
+        }
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(p->ev1, p->stream));
+        std::vector<int> h_ints(3 * (size_t)n_fits);
+        std::vector<double> h_err(n_fits);
+        CU(cudaMemcpyAsync(h_err.data(), d_err, sizeof(double) * n_fits, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaMemcpyAsync(h_ints.data(), d_ints, sizeof(int) * 3 * n_fits, cudaMemcpyDeviceToHost, p->stream));
+        double h_flops = 0;
+        CU(cudaMemcpyAsync(&h_flops, p->d_flops, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+        p->last_ms = ms; p->last_flops = h_flops; p->last_launches = 1;
+        for (int i = 0; i < n_fits; i++) {
+            if (fold_err) fold_err[i] = h_err[i];
+            if (status) status[i] = h_ints[i];
+            if (n_selected) n_selected[i] = h_ints[n_fits + i];
+            if (n_iter) n_iter[i] = h_ints[2 * (size_t)n_fits + i];
+        }
+        if (dump) {   // copy the dump to host-side mirrors allocated by the caller (reuse pointers)
+            int *hm = (int *)malloc(sizeof(int) * (1 + p->cap));
+            double *hb = (double *)malloc(sizeof(double) * (2 * p->cap + 4));
+            CU(cudaMemcpy(hm, dump->m, sizeof(int) * (1 + p->cap), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(hb, dump->beta, sizeof(double) * (2 * p->cap + 4), cudaMemcpyDeviceToHost));
+            dump->m = hm; dump->used = hm + 1; dump->beta = hb; dump->var = hb + p->cap; dump->scalars = hb + 2 * p->cap;
+        }
+        for (int i = 0; i < ns; i++) cudaFree(scratch[i]);
+    } catch (std::pair<int, std::string> &e) {
+        for (int i = 0; i < ns; i++) cudaFree(scratch[i]);
+        return fail(e.first, e.second);
+    }
+    return PAREBEN_OK;
+}
+
+}  // namespace
+
+extern "C" int pareben_run_fits(pareben_problem *p, int n_fits, const int *fold, const double *alpha,
+                                const double *lambda, double *fold_err, int *status, int *n_selected, int *n_iter)
+{
+    return run_fits_impl(p, n_fits, fold, alpha, lambda, fold_err, status, n_selected, n_iter, nullptr);
+}
+
+// Cost-aware interleaving: order fits by falling expected cost (rising lambda,
+// ties by fit number) and deal them round-robin, so every shard gets the same cost mix.
+// Pure host logic (no device needed).
+extern "C" int pareben_shard_plan(const double *lambda, int n_grid, int n_folds, int shard, int n_shards,
+                                  int *fit_index, int *n_mine)
+{
+    if (!lambda || !fit_index || !n_mine || n_grid < 1 || n_folds < 1 || n_shards < 1 || shard < 0 || shard >= n_shards)
+        return fail(PAREBEN_EINVAL, "pareben_shard_plan: bad argument");
+    const int total = n_grid * n_folds;
+    std::vector<int> order(total);
+    for (int i = 0; i < total; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lambda[a / n_folds] < lambda[b / n_folds]; });
+    std::vector<int> mine;
+    for (int r = shard; r < total; r += n_shards) mine.push_back(order[r]);
+    std::sort(mine.begin(), mine.end());
+    for (size_t i = 0; i < mine.size(); i++) fit_index[i] = mine[i];
+    *n_mine = (int)mine.size();
+    return PAREBEN_OK;
+}
+
+extern "C" int pareben_cv_grid(const double *basis, int n, int k, const double *target, const int *fold_id,
+                               int n_folds, const double *alpha, const double *lambda, int n_grid, int epis,
+                               int prior, int device, int shard, int n_shards, double *fold_err,
+                               int *status, int *n_selected)
+{
+    if (n_folds < 1 || n_grid < 1 || !alpha || !lambda || !fold_err) return fail(PAREBEN_EINVAL, "pareben_cv_grid: bad argument");
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(PAREBEN_EINVAL, "pareben_cv_grid: bad shard");
+    const int total = n_grid * n_folds;
+    std::vector<int> mine(total);
+    int m_count = 0;
+    pareben_shard_plan(lambda, n_grid, n_folds, shard, n_shards, mine.data(), &m_count);
+    mine.resize(m_count);
+    const int m = (int)mine.size();
+    if (m == 0) return PAREBEN_OK;
+    pareben_problem *p = nullptr;
+    int rc = pareben_problem_create(&p, device, basis, n, k, target, fold_id, n_folds, epis, prior);
+    if (rc != PAREBEN_OK) return rc;
+    std::vector<int> fold(m), st(m), ns(m);
+    std::vector<double> a(m), l(m), err(m);
+    for (int i = 0; i < m; i++) {
+        const int fit = mine[i];
+        fold[i] = fit % n_folds + 1; a[i] = alpha[fit / n_folds]; l[i] = lambda[fit / n_folds];
+    }
+    rc = pareben_run_fits(p, m, fold.data(), a.data(), l.data(), err.data(), st.data(), ns.data(), nullptr);
+    pareben_problem_destroy(p);
+    if (rc != PAREBEN_OK) return rc;
+    for (int i = 0; i < m; i++) {
+        fold_err[mine[i]] = err[i];
+        if (status) status[mine[i]] = st[i];
+        if (n_selected) n_selected[mine[i]] = ns[i];
+    }
+    return PAREBEN_OK;
+}
+
+extern "C" int pareben_fit(pareben_problem *p, double alpha, double lambda, double *beta_table, double *wald,
+                           double *intercept, double *extra, int *status)
+{
+    if (!p || !beta_table) return fail(PAREBEN_EINVAL, "pareben_fit: bad argument");
+    if (p->n_folds != 0) return fail(PAREBEN_EINVAL, "pareben_fit needs a problem created with n_folds == 0");
+    DumpBuffers dump;
+    int fold = 0, st = 0;
+    double err = 0;
+    int rc = run_fits_impl(p, 1, &fold, &alpha, &lambda, &err, &st, nullptr, nullptr, &dump);
+    if (rc != PAREBEN_OK) return rc;
+    const int k = p->k, kc = p->kc;
+    const int M = dump.m[0];
+    if (p->prior == PAREBEN_GAUSSIAN) {
+        const int ncol = p->epis ? 5 : 4;
+        // loci columns (MainEff.c:87-91, NeFull2.c:100-134)
+        for (int c = 0; c < k; c++) { beta_table[c] = c + 1; beta_table[(size_t)kc + c] = c + 1; }
+        if (p->epis) { size_t kk = k; for (int i = 0; i < k - 1; i++) for (int j = i + 1; j < k; j++, kk++) { beta_table[kk] = i + 1; beta_table[(size_t)kc + kk] = j + 1; } }
+        for (size_t z = (size_t)2 * kc; z < (size_t)ncol * kc; z++) beta_table[z] = 0;
+        for (int i = 0; i < M; i++) {
+            const int c = dump.used[i] - 1;
+            beta_table[(size_t)2 * kc + c] = dump.beta[i];
+            beta_table[(size_t)3 * kc + c] = dump.var[i];
+            if (p->epis) beta_table[(size_t)4 * kc + c] = dump.used[i];
+        }
+        if (intercept) intercept[0] = dump.scalars[1];
+    } else {
+        if (!p->epis) {      // k x 4 indexed by column id (NEmainEff.c:270-291, 364-371)
+            for (int c = 0; c < k; c++) { beta_table[c] = c + 1; beta_table[(size_t)k + c] = c + 1; beta_table[(size_t)2 * k + c] = 0; beta_table[(size_t)3 * k + c] = 0; }
+            for (int i = 0; i < M; i++) { const int c = dump.used[i] - 1; beta_table[(size_t)2 * k + c] = dump.beta[i]; beta_table[(size_t)3 * k + c] = dump.var[i]; }
+        } else {             // compact 2k x 4 in Used order with decoded loci (NeFull.c:168-208)
+            const int rows = 2 * k;
+            for (size_t z = 0; z < (size_t)4 * rows; z++) beta_table[z] = 0;
+            for (int i = 0; i < M && i < rows; i++) {
+                const int c = dump.used[i] - 1;
+                int li = c, lj = c;
+                if (c >= k) { long long pp = (long long)c - k; int ii = 0; while ((long long)(ii + 1) * (2LL * k - (ii + 1) - 1) / 2 <= pp) ii++; li = ii; lj = (int)(pp - (long long)ii * (2LL * k - ii - 1) / 2) + ii + 1; }
+                beta_table[i] = li + 1; beta_table[(size_t)rows + i] = lj + 1;
+                beta_table[(size_t)2 * rows + i] = dump.beta[i]; beta_table[(size_t)3 * rows + i] = dump.var[i];
+            }
+        }
+        if (intercept) { intercept[0] = dump.scalars[1]; intercept[1] = dump.scalars[2]; }
+    }
+    if (wald) wald[0] = dump.scalars[0];
+    if (extra) extra[0] = dump.scalars[3];
+    if (status) status[0] = st;
+    free(dump.m); free(dump.beta);
+    return PAREBEN_OK;
+}
+
+extern "C" int pareben_lambda_max(pareben_problem *p, double *lambda_max)
+{
+    if (!p || !lambda_max) return fail(PAREBEN_EINVAL, "pareben_lambda_max: bad argument");
+    try {
+        CU(cudaSetDevice(p->device));
+        // GetLambdaMax works on ALL rows (R/BuildGrid.R:5-32): build a row-major copy once.
+        const int n = p->n, k = p->k;
+        std::vector<double> y(n);
+        CU(cudaMemcpy(y.data(), p->d_y, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        long double s = 0; for (double v : y) s += v;
+        long double mean = s / n, t = 0; for (double v : y) t += (v - mean);
+        mean += t / n;
+        std::vector<double> centred(n), resp(n);
+        long double ss = 0;
+        for (int i = 0; i < n; i++) { centred[i] = (double)(y[i] - (double)mean); ss += (long double)centred[i] * centred[i]; }
+        const double nrm = std::sqrt((double)ss);
+        for (int i = 0; i < n; i++) resp[i] = centred[i] / nrm;
+        double *d_rows_x = nullptr, *d_resp = nullptr, *d_max = nullptr; int *d_rows = nullptr;
+        CU(cudaMalloc(&d_rows_x, sizeof(double) * (size_t)n * k));
+        CU(cudaMalloc(&d_resp, sizeof(double) * n));
+        CU(cudaMalloc(&d_rows, sizeof(int) * n));
+        std::vector<int> rows(n); for (int i = 0; i < n; i++) rows[i] = i;
+        CU(cudaMemcpy(d_rows, rows.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        gather_rows_kernel<<<dim3((n + 31) / 32, (k + 31) / 32), dim3(32, 8), 0, p->stream>>>(p->d_Xcol, n, k, d_rows, n, d_rows_x);
+        double best = std::log(1.1);
+        auto pass = [&](int c0, int c1, const std::vector<double> &r, bool epis) {
+            const int nb = (c1 - c0 + 255) / 256;
+            if (nb <= 0) return;
+            CU(cudaMemcpyAsync(d_resp, r.data(), sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
+            CU(cudaMalloc(&d_max, sizeof(double) * nb));
+            if (epis) lambda_max_kernel<true><<<nb, 256, 0, p->stream>>>(d_rows_x, n, k, c0, c1, d_resp, d_max);
+            else lambda_max_kernel<false><<<nb, 256, 0, p->stream>>>(d_rows_x, n, k, c0, c1, d_resp, d_max);
+            std::vector<double> hm(nb);
+            CU(cudaMemcpyAsync(hm.data(), d_max, sizeof(double) * nb, cudaMemcpyDeviceToHost, p->stream));
+            CU(cudaStreamSynchronize(p->stream));
+            for (double v : hm) if (v > best) best = v;
+            cudaFree(d_max); d_max = nullptr;
+        };
+        pass(0, k, resp, false);                       // main effects against the normalised response (:14-19)
+        if (p->epis) pass(k, p->kc, centred, true);    // pairs against the UN-normalised centred response (:24-27)
+        cudaFree(d_rows_x); cudaFree(d_resp); cudaFree(d_rows);
+        *lambda_max = best;
+    } catch (std::pair<int, std::string> &e) {
+        return fail(e.first, e.second);
+    }
+    return PAREBEN_OK;
+}
+
+extern "C" int pareben_last_counters(pareben_problem *p, double *flops, double *kernel_ms, int *launches)
+{
+    if (!p) return fail(PAREBEN_EINVAL, "null problem");
+    if (flops) *flops = p->last_flops;
+    if (kernel_ms) *kernel_ms = p->last_ms;
+    if (launches) *launches = p->last_launches;
+    return PAREBEN_OK;
+}
+
+// FP64 peak probes used by bench.py for the roofline denominator (MEASURED_PEAKS.json has no
+// FP64 entry).  which: 0 = DFMA (CUDA cores), 1 = DMMA (mma.sync m8n8k4 f64).
+extern "C" int pareben_measure_fp64_peak(int device, int which, double *tflops)
+{
+    if (!tflops) return fail(PAREBEN_EINVAL, "null output");
+    if (pareben_device_count() <= device || device < 0) return fail(PAREBEN_ENODEVICE, "no usable CUDA device");
+    try {
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+        double *d = nullptr;
+        CU(cudaMalloc(&d, sizeof(double) * blocks * threads));
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        double best = 0;
+        for (int rep = 0; rep < 5; rep++) {
+            CU(cudaEventRecord(e0));
+            if (which == 0) dfma_peak_kernel<<<blocks, threads>>>(d, iters);
+            else dmma_peak_kernel<<<blocks, threads>>>(d, iters);
+            CU(cudaEventRecord(e1));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            double fl = which == 0 ? 2.0 * 8 * iters * (double)blocks * threads
+                                   : 2.0 * 8 * 8 * 4 * 4 * iters * (double)blocks * (threads / 32);
+            if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+        *tflops = best;
+    } catch (std::pair<int, std::string> &e) {
+        return fail(e.first, e.second);
+    }
+    return PAREBEN_OK;
+}

@@ -1,0 +1,156 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C-ABI, against the reference's results.
+
+Expected values are the committed golden vectors (produced by the reference's own C, see
+tests/golden/make_golden.py) and, where oracle/_ref or the C restatement is loadable on the box,
+live oracle fits on fresh inputs.  Tolerance: the path is FP64; reductions are re-associated
+relative to OpenBLAS, so per-fit errors must agree to rel 1e-8 (north_star's bound) and the
+discrete outputs (support sizes, selected alpha/lambda) must be identical.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import rlayer as R
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def pb(built):
+    import pareben_b200 as pb
+    if pb.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu suite must run on the B200 box")
+    return pb
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def test_config1_gaussian_full_grid(pb, bundled):
+    g = golden("config1_gaussian.npz")
+    X, y = bundled["BASIS"][:50, :100].astype(float), bundled["y"][:50]
+    err, st, ns = pb.cv_grid(X, y, g["fold_id"], 3, g["grid_alpha"], g["grid_lambda"])
+    assert np.all(st == 0)
+    assert np.array_equal(ns, g["n_selected"]), f"{(ns != g['n_selected']).sum()} fits with a different support size"
+    assert _rel(err, g["fold_err"]) < RTOL
+    out = pb.CrossValidate(X, y, 3)
+    assert out["alpha.optimal"] == float(g["alpha_optimal"])
+    assert abs(out["lambda.optimal"] - float(g["lambda_optimal"])) <= 1e-13 * float(g["lambda_optimal"])
+    assert _rel(out["Results.Summary"]["MSE"], g["summary_mse"]) < RTOL
+    assert _rel(out["Results.Summary"]["SE"], g["summary_se"]) < 1e-6
+    assert np.allclose(out["Results.Summary"]["alpha"], g["summary_alpha"])
+    loc = pb.CrossValidate(X, y, 3, foldId=g["fold_id"], search="local")
+    assert loc["alpha.optimal"] == float(g["local_alpha"])
+    assert abs(loc["lambda.optimal"] - float(g["local_lambda"])) <= 1e-13 * float(g["local_lambda"])
+    assert np.array_equal(loc["fullCV"][:, 1] != 0, g["local_full"][:, 1] != 0)       # same early stops
+    assert np.allclose(loc["fullCV"], g["local_full"], rtol=1e-8, atol=0)
+
+
+def test_grid_and_lambda_max_on_device(pb, bundled):
+    for (n, k, epis) in ((50, 100, False), (120, 25, True), (1000, 481, False)):
+        X, y = bundled["BASIS"][:n, :k].astype(float), bundled["y"][:n]
+        want = R.get_lambda_max(X, y, epis)
+        got = pb.GetLambdaMax(X, y, "yes" if epis else "no")
+        assert abs(got - want) <= 1e-12 * abs(want)
+        ga, gl = R.build_grid(X, y, 3, epis)
+        grid = pb.BuildGrid(X, y, 3, "yes" if epis else "no")
+        assert np.array_equal(grid["alpha"], ga) and np.allclose(grid["lambda"], gl, rtol=1e-12, atol=0)
+
+
+def test_bundled_gaussian_rows(pb, bundled):
+    g = golden("gauss_bundled_sample.npz")
+    X, y = bundled["BASIS"].astype(float), bundled["y"]
+    rows = g["rows"]
+    err, st, ns = pb.cv_grid(X, y, g["fold_id"], 3, g["grid_alpha"][rows], g["grid_lambda"][rows])
+    assert np.all(st == 0)
+    assert np.array_equal(ns, g["n_selected"])
+    assert _rel(err, g["fold_err"]) < RTOL
+
+
+def test_gaussian_epis_slice(pb, bundled):
+    g = golden("gauss_epis_slice.npz")
+    X, y = bundled["BASIS"][:120, :25].astype(float), bundled["y"][:120]
+    rows = g["rows"]
+    err, st, ns = pb.cv_grid(X, y, g["fold_id"], 3, g["grid_alpha"][rows], g["grid_lambda"][rows], epis=True)
+    assert np.array_equal(ns, g["n_selected"])
+    assert _rel(err, g["fold_err"]) < RTOL
+
+
+def test_final_model_layout(pb, bundled):
+    g = golden("final_gaussian_config1.npz")
+    X, y = bundled["BASIS"][:50, :100].astype(float), bundled["y"][:50]
+    with pb.Problem(X, y, None, 0, False, "gaussian") as p:
+        table, wald, icpt, resid, st = p.fit(float(g["alpha"]), float(g["lam"]))
+    ref = g["raw_beta"]
+    assert table.shape == ref.shape == (100, 4)
+    assert np.array_equal(table[:, :2], ref[:, :2])
+    assert np.array_equal(table[:, 2] != 0, ref[:, 2] != 0)
+    assert np.allclose(table[:, 2:], ref[:, 2:], rtol=1e-8, atol=1e-14)
+    assert abs(icpt[0] - g["intercept"][0]) <= 1e-10 * abs(g["intercept"][0])
+    assert abs(resid - float(g["resid_var"])) <= 1e-8 * float(g["resid_var"])
+    assert abs(wald - float(g["wald"])) <= 1e-8 * abs(float(g["wald"]))
+    fit = pb.EBelasticNet_Gaussian(X, y, float(g["lam"]), float(g["alpha"]))
+    assert fit["weight"].shape[1] == 6 and fit["weight"].shape[0] == int((ref[:, 2] != 0).sum())
+
+
+def test_live_oracle_random_inputs(pb):
+    """Fresh seeded inputs (ragged fold sizes, a duplicated column, an all-zero column) against
+    whichever oracle library is present on this box."""
+    lib = R.fit_lib(R.available_kind())
+    rng = np.random.default_rng(11)
+    n, k = 101, 40
+    X = rng.choice([-1.0, 0.0, 1.0], size=(n, k), p=[0.25, 0.5, 0.25])
+    X[:, 17] = X[:, 4]            # exact duplicate: ties must resolve to the lower index
+    X[:, 23] = 0.0                # all-zero column: scale forced to 1
+    y = 50 + 3 * X[:, 4] - 2 * X[:, 9] + rng.normal(0, 1.5, n)
+    folds = R.assign_to_folds(n, 4)
+    lam = np.array([3.0, 0.8, 0.2, 0.05, 0.01]); alpha = np.array([1.0, 0.7, 0.5, 0.2, 0.05])
+    err, st, ns = pb.cv_grid(X, y, folds, 4, alpha, lam)
+    for i in range(lam.size):
+        for f in range(1, 5):
+            e, fit = R.fit_one(X, y, folds, f, lam[i], alpha[i], lib=lib)
+            m = 0 if fit.weight[0, 0] == 0 else fit.weight.shape[0]
+            assert ns[i, f - 1] == m
+            assert abs(err[i, f - 1] - e) <= RTOL * abs(e)
+
+
+def test_full_size_properties(pb, bundled):
+    """Size-independent properties at the bundled full size (1000 x 481, 10 folds): the table is
+    bitwise reproducible, independent of batch composition/order, and shards merge exactly."""
+    X, y = bundled["BASIS"].astype(float), bundled["y"]
+    folds = pb.AssignToFolds(X, 10)
+    grid = pb.BuildGrid(X, y, 10)
+    rows = np.arange(0, 400, 16)
+    a, l = grid["alpha"][rows], grid["lambda"][rows]
+    e1, s1, n1 = pb.cv_grid(X, y, folds, 10, a, l)
+    e2, _, _ = pb.cv_grid(X, y, folds, 10, a, l)
+    assert np.array_equal(e1, e2)                                   # run-to-run bitwise
+    perm = np.random.default_rng(0).permutation(rows.size)
+    e3, _, _ = pb.cv_grid(X, y, folds, 10, a[perm], l[perm])
+    assert np.array_equal(e3, e1[perm])                             # batch order does not matter
+    merged = np.zeros_like(e1)
+    for r in range(3):
+        es, _, _ = pb.cv_grid(X, y, folds, 10, a, l, shard=r, n_shards=3)
+        merged += es
+    assert np.array_equal(merged, e1)                               # 3 shards == 1 shard, bitwise
+    assert np.all(np.isfinite(e1)) and np.all(e1 > 0) and np.all(s1 == 0)
+    # SSE at the largest lambda equals the intercept-only prediction error when nothing is selected
+    empty = n1 == 0
+    for i, f in zip(*np.nonzero(empty)):
+        te = folds == f + 1
+        tr = ~te
+        assert abs(e1[i, f] - np.sum((y[te] - y[tr].mean()) ** 2)) <= 1e-9 * e1[i, f]
+
+
+def test_edge_cases(pb):
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(30, 6)); y = rng.normal(size=30) + 10
+    folds = np.arange(30) % 3 + 1
+    with pytest.raises(pb.ParebenError):
+        pb.cv_grid(X, y, np.zeros(30, np.int32), 3, np.ones(1), np.ones(1))          # fold labels out of range
+    err, st, ns = pb.cv_grid(X, y, folds, 3, np.ones(1), np.array([1e6]))           # huge lambda: empty model
+    assert np.all(np.isfinite(err))
+    err2, _, _ = pb.cv_grid(X[:, :1], y, folds, 3, np.ones(2), np.array([1.0, 0.01]))   # K = 1
+    assert err2.shape == (2, 3) and np.all(np.isfinite(err2))

@@ -1,0 +1,131 @@
+"""CPU suite, part 1: the oracle itself is pinned before anything trusts it.
+ * R RNG emulator against R's documented known answers.
+ * R-layer restatement against the CrossValidate output the reference's authors published
+   (paper_materials/.../LooserSubset_10000_ParCV_5-3-2018.RDS -> tests/golden/published_cv_10000.npz).
+ * C restatement (oracle/eben_*.c) against golden vectors produced by the reference's own C.
+ * Where oracle/_ref is present (build container), restatement vs reference live on fresh inputs.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import rlayer as R
+from oracle.rrng import RRng
+
+
+def test_rrng_known_answers():
+    assert RRng(1, "Rejection").sample_int(10) == [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]    # R >= 3.6.0
+    assert RRng(1, "Rounding").sample_int(10) == [3, 4, 5, 7, 2, 8, 9, 6, 10, 1]     # R < 3.6.0
+    assert abs(RRng(1).unif_rand() - 0.2655086631421) < 1e-12                         # set.seed(1); runif(1)
+    g = golden("rrng.npz")
+    assert list(R.assign_to_folds(50, 3)[:12]) == [1, 3, 1, 1, 2, 1, 2, 3, 3, 3, 2, 1]
+    assert list(R.assign_to_folds(500, 5)[:12]) == [4, 2, 4, 3, 1, 4, 5, 1, 2, 2, 1, 5]
+    assert np.array_equal(R.assign_to_folds(1000, 10), g["folds_1000_10"])
+    for nf, n in ((3, 50), (5, 500), (10, 1000)):
+        f = R.assign_to_folds(n, nf)
+        assert np.bincount(f)[1:].max() - np.bincount(f)[1:].min() <= 1
+
+
+def test_published_cv_table_semantics():
+    """Grid values, row order, SE formula and argmin rule against the authors' saved output."""
+    p = golden("published_cv_10000.npz")
+    alpha = R.r_seq(1.0, 0.05, -0.05)
+    assert np.array_equal(np.unique(p["detail_alpha"]), np.sort(alpha))         # bit-for-bit alpha grid
+    lam = np.unique(p["detail_lambda"])[::-1]
+    lam_max = lam[0]
+    lam_min = math.log(0.001 * lam_max)
+    mine = np.exp(R.r_seq(math.log(lam_max), lam_min, -(math.log(lam_max) - lam_min) / 19))
+    assert np.allclose(mine, lam, rtol=1e-13, atol=0)
+    # detail rows: grid-row major (alpha fastest within lambda), fold minor
+    assert np.array_equal(p["detail_fold"][:6], [1, 2, 3, 1, 2, 3])
+    assert np.allclose(p["detail_alpha"][:9], np.repeat(alpha[:3], 3))
+    n_folds = 3
+    fold_err = p["detail_mse"].reshape(400, n_folds)
+    ga = p["detail_alpha"].reshape(400, n_folds)[:, 0]
+    gl = p["detail_lambda"].reshape(400, n_folds)[:, 0]
+    s = R.summarise(ga, gl, fold_err)
+    assert np.allclose(s["alpha"], p["summary_alpha"]) and np.allclose(s["lambda"], p["summary_lambda"])
+    assert np.allclose(s["MSE"], p["summary_mse"], rtol=1e-13)
+    assert np.allclose(s["SE"], p["summary_se"], rtol=1e-10)
+    a, l, _ = R.select_optimum(s)
+    assert a == float(p["alpha_optimal"][0]) and l == float(p["lambda_optimal"][0])
+
+
+def _port_table(X, y, n_folds, epis, g, kind="port"):
+    lib = R.fit_lib(kind)
+    out = np.zeros_like(g["fold_err"]); ns = np.zeros_like(g["n_selected"])
+    for i, r in enumerate(g["rows"]):
+        for f in range(1, n_folds + 1):
+            e, fit = R.fit_one(X, y, g["fold_id"], f, g["grid_lambda"][r], g["grid_alpha"][r], epis, "gaussian", lib)
+            out[i, f - 1] = e
+            ns[i, f - 1] = 0 if fit.weight[0, 0] == 0 else fit.weight.shape[0]
+    return out, ns
+
+
+def test_port_gaussian_config1_matches_reference_golden(bundled, built):
+    g = golden("config1_gaussian.npz")
+    X, y = bundled["BASIS"][:50, :100].astype(float), bundled["y"][:50]
+    ga, gl = R.build_grid(X, y, 3)
+    assert np.allclose(ga, g["grid_alpha"], rtol=0, atol=0) and np.allclose(gl, g["grid_lambda"], rtol=1e-14)
+    assert abs(gl[0] - 2.5115842672973) < 1e-12 and abs(gl[-1] - 0.0025115842672973) < 1e-15
+    err, ns = _port_table(X, y, 3, False, g)
+    assert np.array_equal(ns, g["n_selected"])
+    assert np.max(np.abs(err - g["fold_err"]) / np.abs(g["fold_err"])) < 1e-10
+    s = R.summarise(ga, gl, err)
+    a, l, _ = R.select_optimum(s)
+    assert a == 1.0 and abs(l - 0.0222492909371512) < 1e-14
+    assert abs(s["MSE"].min() - 1919.181608760305) < 1e-6
+    # anchors printed in SURVEY D.1
+    assert np.allclose(g["fold_err"][0], [2246.40804244, 2004.15893851, 1558.65730397], rtol=1e-10)
+    assert np.allclose(g["fold_err"][399], [2131.74032709, 3156.56558406, 3180.85087744], rtol=1e-10)
+    assert list(g["n_selected"][399]) == [9, 8, 9]
+
+
+def test_port_gaussian_epis_slice(bundled, built):
+    g = golden("gauss_epis_slice.npz")
+    X, y = bundled["BASIS"][:120, :25].astype(float), bundled["y"][:120]
+    err, ns = _port_table(X, y, 3, True, g)
+    assert np.array_equal(ns, g["n_selected"])
+    assert np.max(np.abs(err - g["fold_err"]) / np.abs(g["fold_err"])) < 1e-10
+
+
+def test_port_gaussian_bundled_rows(bundled, built):
+    g = golden("gauss_bundled_sample.npz")
+    X, y = bundled["BASIS"].astype(float), bundled["y"]
+    sub = {k: g[k] for k in g.files}
+    keep = [0, 3, 9, 17]            # a cheap subset incl. the last (largest active set) row
+    sub["rows"] = g["rows"][keep]; sub["fold_err"] = g["fold_err"][keep]; sub["n_selected"] = g["n_selected"][keep]
+    err, ns = _port_table(X, y, 3, False, sub)
+    assert np.array_equal(ns, sub["n_selected"])
+    assert np.max(np.abs(err - sub["fold_err"]) / np.abs(sub["fold_err"])) < 1e-9
+
+
+def test_local_search_replay_shape_and_rule():
+    g = golden("config1_gaussian.npz")
+    each, a, l, full = R.local_search_replay(g["grid_alpha"], g["grid_lambda"], g["fold_err"])
+    assert each.shape == (20, 4) and full.shape == (400, 4)
+    assert np.array_equal(each, g["local_cv"]) and a == float(g["local_alpha"]) and l == float(g["local_lambda"])
+    visited = int((full[:, 1] != 0).sum())
+    assert 20 <= visited <= 400 and np.all(full[visited:] == 0)
+    # first step of every alpha can never stop (previousL = 2e10), so each alpha visits >= 2 lambdas or all
+    assert np.all(each[:, 2] <= 1e10)
+
+
+@pytest.mark.skipif(not os.path.exists(R.REF_LIB), reason="oracle/_ref is only built where /root/reference exists")
+def test_port_vs_reference_live_random(built):
+    rng = np.random.default_rng(7)
+    X = rng.choice([-1.0, 0.0, 1.0], size=(80, 30), p=[0.25, 0.5, 0.25])
+    y = 100 + X[:, 3] * 4 - X[:, 11] * 3 + X[:, 5] * X[:, 7] * 3 + rng.normal(0, 2, 80)
+    for epis in (False, True):
+        for lam, a in ((2.0, 1.0), (0.3, 0.5), (0.02, 0.1)):
+            f2 = R.eb_elastic_net_gaussian(X, y, lam, a, epis, R.fit_lib("port"))
+            if epis and f2.weight.shape[0] >= 50:
+                continue    # the reference writes past basisMax = 2K here and corrupts its heap
+            f1 = R.eb_elastic_net_gaussian(X, y, lam, a, epis, R.fit_lib("reference"))
+            assert f1.weight.shape == f2.weight.shape
+            assert np.allclose(f1.weight[:, :4], f2.weight[:, :4], rtol=1e-8, atol=1e-12)
+            assert abs(f1.intercept[0] - f2.intercept[0]) < 1e-9 * abs(f1.intercept[0])
+            assert abs(f1.wald - f2.wald) <= 1e-8 * max(1.0, abs(f1.wald))
