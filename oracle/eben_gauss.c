@@ -437,7 +437,8 @@ static void inner_solver(State *s, const Variant *v, const double *t, double lam
                 if (selected == ACT_REEST || selected == ACT_DEL)
                     for (int i = 0; i < s->M; i++) if (s->used[i] == nu + 1) { jj = i; break; }
                 column(s, nu, phi_new);
-                for (int h = 0; h < N; h++) phi_new[h] *= 1 / s->scale[nu];
+                if (s->loc1[nu] == s->loc2[nu]) for (int h = 0; h < N; h++) phi_new[h] *= 1 / s->scale[nu];   /* dscal by 1/s (:516-520) */
+                else for (int h = 0; h < N; h++) phi_new[h] = phi_new[h] / s->scale[nu];                       /* pairs: x/s (NeFull2.c:277-290) */
                 if (selected == ACT_REEST && fabs(log(new_alpha) - log(s->alpha[jj])) <= v->reest_tol && !d.any_delete)
                     selected = ACT_TERM;
                 int updated = 0;

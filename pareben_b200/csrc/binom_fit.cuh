@@ -1,14 +1,504 @@
-// binom_fit.cuh -- one Binomial (logistic) EBEN fit per thread block.  (stub: filled in next)
+// binom_fit.cuh -- one Binomial (logistic) EBEN fit per thread block (main-effect and Epis).
+//
+// Device re-design of the reference's logistic solver; behaviour follows
+//   /root/reference/EBEN_orig/src/ElasticNetBinaryNEmainEff.c (entry :236-389, inner solver
+//   :397-827, ActionAdd :830-1003, ActionDel :1010-1121, ActionRes :1127-1203, init :1215-1406,
+//   FullStat :1633-1803, PostMode/IRLS :1808-2010, DeltaML :2063-2238) and
+//   ElasticNetBinaryNeFull.c for Epis (same skeleton; clamps and constants per SURVEY.md App. A),
+// followed by the hold-out score of /root/reference/R/GetModelError.R:34-57.
+// Differences in kind, not in result:
+//  * FullStat's per-candidate vector BASIS'B PHI (:1693-1702) is computed once as a blocked
+//    contraction and KEPT as a cache G for the block of actions that follows; the reference
+//    recomputes it from scratch inside every action (:967-987, 1040-1058, 1171-1194) even though
+//    the IRLS weights B cannot change until the next FullStat.
+//  * the S/Q corrections of the LAST action of a block are skipped: FullStat overwrites S and Q
+//    immediately afterwards (:749-762), so they are dead in the reference too.
+//  * dgelsy on the N x 2 start-up regression is a closed-form pivoted QR; dpotrf/dpotri is the
+//    in-block symmetric sweep.
 #pragma once
 #include "common.cuh"
+#include "gauss_fit.cuh"
+
 namespace pareben {
+
+struct BinomState {
+    int M;            // intercept + active effects
+    int n_unused;
+    int status;
+    double flops;
+};
+
+// eta = PHI mu ; y = sigmoid(eta) ; returns the data error (NEmainEff.c:2013-2032)
+__device__ inline double predictor_and_error(const Slab &s, int N, int M, const double *mu, const double *t,
+                                             double *eta, double *yv, const Scratch &sc)
+{
+    double err = 0;
+    for (int h = threadIdx.x; h < N; h += blockDim.x) {
+        double z = 0;
+        for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * N + h], mu[j], z);
+        eta[h] = z;
+        const double y = 1 / (1 + exp(-z));
+        yv[h] = y;
+        double e = 0;
+        if (y != 0) e = e - t[h] * log(y);
+        if (y != 1) e = e - (1 - t[h]) * log(1 - y);
+        err += e;
+    }
+    return block_sum(err, sc);
+}
+
+template <bool EPIS>
+__device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t, const Scratch &sc)
+{   // fEBCatPostMode*: Newton steps with step halving (NEmainEff.c:1808-2010, NeFull.c:998-1152)
+    const int M = b.M, T = blockDim.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2, *g = s.gamma, *dmu = s.u, *mun = s.tmp;
+    double derr = predictor_and_error(s, N, M, s.mu, t, eta, yv, sc);
+    double reg = 0;
+    for (int i = 1; i < M; i++) reg = reg + s.alpha[i - 1] * s.mu[i] * s.mu[i] / 2;
+    double total = reg + derr;
+    for (int it = 0; it < 25; it++) {
+        const double err_log = total;
+        double g0 = 0, h0 = 0;
+        for (int h = threadIdx.x; h < N; h += T) {
+            double y = yv[h];
+            if (EPIS) { if (y < 1e-5) y = 1e-5; if (y > (1 - 1e-5)) y = 1 - 1e-5; yv[h] = y; }     // NeFull.c:1049-1050
+            const double eh = t[h] - y;
+            e[h] = eh; g0 += eh;
+            double bw = y * (1 - y);
+            if (!EPIS) { if (bw < 1e-10) bw = 1e-5; if (bw > 1e10) bw = 1e5; }                      // NEmainEff.c:1880-1882
+            else { if (bw < 1e-5) bw = 1e-3; if (bw > 1e5) bw = 1e3; }                              // NeFull.c:1054-1055
+            w[h] = bw; h0 += bw;
+        }
+        block_sum2(g0, h0, sc);
+        if (threadIdx.x == 0) { g[0] = g0; s.H[0] = h0; }
+        __syncthreads();
+        // gradient, first row/column, and the upper triangle of PHI' B PHI (+ diag(alpha)); one warp per entry
+        const int m1 = M - 1, npair = m1 * (m1 + 1) / 2;
+        for (int p = wid; p < m1 + npair; p += nw) {
+            if (p < m1) {
+                const int j = p + 1;
+                const double *ph = s.phi + (size_t)j * N;
+                double gj = 0, hj = 0;
+                for (int h = lane; h < N; h += 32) { gj = fma(ph[h], e[h], gj); hj = fma(w[h], ph[h], hj); }
+                gj = warp_sum(gj); hj = warp_sum(hj);
+                if (lane == 0) { g[j] = gj - s.alpha[j - 1] * s.mu[j]; s.H[j] = hj; s.H[j * M] = hj; }
+            } else {
+                const int q = p - m1;
+                int k = (int)floor((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+                while ((k + 1) * (k + 2) / 2 <= q) k++;
+                while (k * (k + 1) / 2 > q) k--;
+                const int j = q - k * (k + 1) / 2;            // j <= k, both 0-based over effects
+                const double *a = s.phi + (size_t)(j + 1) * N, *c = s.phi + (size_t)(k + 1) * N;
+                double z = 0;
+                for (int h = lane; h < N; h += 32) z = fma(a[h] * w[h], c[h], z);
+                z = warp_sum(z);
+                if (lane == 0) {
+                    if (j == k) z += s.alpha[k];
+                    s.H[(k + 1) * M + (j + 1)] = z; s.H[(j + 1) * M + (k + 1)] = z;
+                }
+            }
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < M * M; idx += T) s.sigma[idx] = s.H[idx];
+        __syncthreads();
+        if (!spd_inverse_sweep(s.sigma, M, s.colk, sc)) b.status |= ST_NOT_PD;
+        int cnt = 0;
+        for (int j = EPIS ? 0 : 1; j < M; j++) cnt += fabs(g[j]) < 1e-6;
+        for (int k = threadIdx.x; k < M; k += T) {
+            double z = 0;
+            for (int L = 0; L < M; L++) z = fma(s.sigma[L * M + k], g[L], z);
+            dmu[k] = z;
+        }
+        __syncthreads();
+        if (cnt == (EPIS ? M : M - 1)) break;
+        double step = 1;
+        while (step > 1.0 / 256) {
+            for (int j = threadIdx.x; j < M; j += T) mun[j] = s.mu[j] + step * dmu[j];
+            __syncthreads();
+            derr = predictor_and_error(s, N, M, mun, t, eta, yv, sc);
+            reg = 0;
+            for (int j = 1; j < M; j++) reg = reg + s.alpha[j - 1] * mun[j] * mun[j] / 2;
+            total = derr + reg;
+            if (total >= err_log) step = step / 2;
+            else {
+                __syncthreads();
+                for (int j = threadIdx.x; j < M; j += T) s.mu[j] = mun[j];
+                step = 0;
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) b.flops += 0;   // IRLS work is not counted in the score-pass model
+}
+
+template <bool EPIS>
+__device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab &s, BinomState &b, double *sV,
+                                       const Scratch &sc)
+{   // fEBCatFullStat* (NEmainEff.c:1633-1803, NeFull.c:848-993)
+    const int N = F.ntr, K = P.K, Kc = P.Kc, T = blockDim.x;
+    const double *X = F.Xtr, *t = F.ytr, *scale = F.scale;
+    post_mode<EPIS>(s, b, N, t, sc);
+    const int M = b.M;
+    double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2;
+    for (int h = threadIdx.x; h < N; h += T) {
+        double z = 0;
+        for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * N + h], s.mu[j], z);
+        eta[h] = z;
+        const double y = 1 / (1 + exp(-z));
+        yv[h] = y;
+        e[h] = t[h] - y;
+    }
+    __syncthreads();
+    // G[p][c] = sum_h x_c[h] phi_p[h] w[h] / s_c   (BPvector, :1693-1702) -- kept as the action cache
+    contract<EPIS>(X, N, K, Kc, M,
+        [&](int r) -> const double * { return s.phi + (size_t)r * N; },
+        [&](int r, int c, double acc) { s.G[(size_t)s.grow[r] * Kc + c] = acc / scale[c]; }, sV, w);
+    for (int c = threadIdx.x; c < Kc; c += T) {
+        Cand<EPIS> cd(c, K);
+        double bb = 0, ze = 0;
+        const double *xr = X;
+        for (int h = 0; h < N; h++, xr += K) { const double x = cd.at(xr); bb = fma(w[h], x * x, bb); ze = fma(x, e[h], ze); }
+        double quad = 0;
+        for (int p = 0; p < M; p++) {
+            const double *sp = s.sigma + p * M;
+            double z = 0;
+            for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sp[j], z);
+            quad = fma(z, s.G[(size_t)s.grow[p] * Kc + c], quad);
+        }
+        const double sc_c = scale[c];
+        s.S_in[c] = bb / (sc_c * sc_c) - quad;
+        s.Q_in[c] = ze / sc_c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) b.flops += 2.0 * N * (double)Kc * (M + 2) + (double)Kc * (2.0 * M * M + M);
+    refresh_out(s, M - 1, Kc);
+}
+
 template <bool EPIS>
 __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v, Slab &s, double lambda,
                           double alpha_en, const FitTask &task, const FitOutputs &out, double *sV, const Scratch &sc)
 {
-    if (threadIdx.x == 0) {
-        if (out.fold_err) out.fold_err[task.out_index] = nan("");
-        if (out.status) out.status[task.out_index] = ST_NONFINITE;
+    const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x;   // cap counts the intercept slot
+    const double *X = F.Xtr, *t = F.ytr, *scale = F.scale;
+    BinomState b; b.M = 2; b.n_unused = 0; b.status = 0; b.flops = 0;
+    for (int j = threadIdx.x; j < cap + 1; j += T) { if (j < cap) s.grow[j] = j; s.alpha[j] = 0; s.mu[j] = 0; }
+    __syncthreads();
+    double vk = 1e-30, vk0, err = 1000, loglik = 0;
+    int iter = 0;
+    while (iter < 100 && err > 1e-8) {                                        // NEmainEff.c:329-344
+        iter++;
+        vk0 = vk;
+        // ------------------------- inner solver (fEBBinaryMex*, :397-827) -------------------------
+        int ini_removed = 1;
+        if (iter <= 1) {                                                      // initialisation, :1239-1385
+            ini_removed = 0;
+            b.M = 2;
+            if (threadIdx.x == 0) s.used[0] = 1;
+            const double sc0 = scale[0], isc = 1 / sc0;
+            for (int h = threadIdx.x; h < N; h += T) {
+                s.phi[h] = 1;
+                const double x = X[(size_t)h * K];
+                s.phi[(size_t)N + h] = EPIS ? x / sc0 : x * isc;              // NeFull.c:93 vs NEmainEff.c:1347-1350
+            }
+            __syncthreads();
+            // least squares of [1 phi] on the pseudo-logits (dgelsy with rcond 1e-5, :1366-1370):
+            // pivoted QR with the ones column leading (its norm sqrt(N) >= ||phi|| = 1)
+            const double *ph = s.phi + N;
+            double sphi = 0, sz = 0;
+            for (int h = threadIdx.x; h < N; h += T) {
+                const double tp = 2 * t[h] - 1, pp = (tp * 0.9 + 1) / 2;
+                const double z = log(pp / (1 - pp));
+                s.e[h] = z;
+                sphi += ph[h]; sz += z;
+            }
+            block_sum2(sphi, sz, sc);
+            const double r11 = sqrt((double)N), r12 = sphi / r11, c1 = sz / r11;
+            double r22 = 0, c2 = 0;
+            for (int h = threadIdx.x; h < N; h += T) { const double vv = ph[h] - r12 / r11; r22 = fma(vv, vv, r22); c2 = fma(vv, s.e[h], c2); }
+            block_sum2(r22, c2, sc);
+            r22 = sqrt(r22);
+            const double f = r11 * r11 + r12 * r12 + r22 * r22, dd = r11 * r22;
+            const double disc = sqrt(fmax(f * f - 4 * dd * dd, 0.0));
+            const double smax = sqrt((f + disc) / 2), smin = smax > 0 ? fabs(dd) / smax : 0;
+            double w0, w1;
+            if (r22 > 0 && smax * 1e-5 <= smin) { w1 = c2 / (r22 * r22); w0 = (c1 - r12 * w1) / r11; }
+            else { const double den = r11 * r11 + r12 * r12; w0 = r11 * c1 / den; w1 = r12 * c1 / den; }
+            double a = w1 == 0 ? 1 : 1 / (w1 * w1);
+            if (a < v.init_alpha_min) a = v.init_alpha_min;
+            if (a > v.init_alpha_max) a = v.init_alpha_max;
+            __syncthreads();
+            if (threadIdx.x == 0) { s.mu[0] = w0; s.mu[1] = w1; s.alpha[0] = a; }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < Kc; c += T) s.amap[c] = -1;
+        __syncthreads();
+        for (int j = threadIdx.x; j < b.M - 1; j += T) s.amap[s.used[j] - 1] = j;
+        __syncthreads();
+        b.n_unused = block_compact(Kc, [&](int c) { return s.amap[c] < 0; }, s.unused, s.upos, 1, sc);
+        const int initial = s.used[0];
+        binom_full_stat<EPIS>(P, F, s, b, sV, sc);
+        int selected = ACT_NONE, last = 0, n_update = 0, jj = -1, i_iter = 0;
+        const int it_max = iter == 1 ? 10 : 100;
+        loglik = 1e-30;
+        while (!last) {
+            i_iter++;
+            const double logl0 = loglik;
+            Decision d = delta_ml<EPIS, true>(s, b.M - 1, N, Kc, lambda, alpha_en, 0.0, 0.0, iter, i_iter, sc);
+            int nu = d.nu, worthwhile;
+            if (selected == ACT_TERM && !ini_removed && b.M > 2) nu = -1;             // :559-563
+            if (nu == -1 && ini_removed) { worthwhile = 0; selected = ACT_TERM; }
+            else if (nu == -1 && !ini_removed && b.M > 2) {                           // :570-579
+                worthwhile = 1; nu = initial - 1;
+                __syncthreads();
+                if (threadIdx.x == 0) { s.action[nu] = ACT_DEL; s.block[0] = nu; }
+                __syncthreads();
+                n_update = 1; ini_removed = 1; selected = ACT_DEL;
+            } else {
+                worthwhile = 1;
+                const int best_is_add = s.action[nu] == ACT_ADD, best_is_del = s.action[nu] == ACT_DEL;
+                double cutoff = d.best * (best_is_add ? v.n_add : 1.0);
+                if (cutoff < v.ml_delta) cutoff = v.ml_delta;
+                n_update = block_compact(Kc, [&](int c) { return s.dml[c] >= cutoff; }, s.block, nullptr, 0, sc);
+                if (best_is_del && n_update > 1) n_update = 1;                        // :607
+                if (n_update == 0) worthwhile = 0;
+            }
+            if (!worthwhile) selected = ACT_TERM;
+            if (worthwhile) {
+                for (int iu = 0; iu < n_update; iu++) {
+                    __syncthreads();
+                    nu = s.block[iu];
+                    selected = s.action[nu];
+                    const double new_alpha = s.aroot[nu];
+                    const bool need_sq = iu != n_update - 1;      // S/Q only matter to later actions of this block
+                    if (selected == ACT_REEST || selected == ACT_DEL) {
+                        const int a = s.amap[nu];
+                        if (a >= 0) jj = a;                        // stale jj kept when the search fails (:629-636)
+                        if (jj < 0 || jj >= b.M - 1) { b.status |= ST_NOT_PD; selected = ACT_TERM; }
+                    }
+                    if (selected == ACT_REEST && fabs(log(new_alpha) - log(s.alpha[jj])) <= v.reest_tol && !d.any_delete)
+                        selected = ACT_TERM;                                          // :663-670
+                    const int M = b.M;
+                    if (selected == ACT_REEST) {                                      // ActionRes*, :1127-1203
+                        const int j1 = jj + 1;
+                        const double old = s.alpha[jj];
+                        const double kappa = 1.0 / (s.sigma[j1 * M + j1] + 1.0 / (new_alpha - old));
+                        const double mujj = s.mu[j1];
+                        const double *sj = s.sigma + j1 * M;
+                        __syncthreads();
+                        if (threadIdx.x == 0) s.alpha[jj] = new_alpha;
+                        for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mujj * kappa * sj[i];
+                        for (int idx = threadIdx.x; idx < M * M; idx += T) {
+                            const int j = idx / M, i = idx - j * M;
+                            s.sigma_new[idx] = s.sigma[idx] - kappa * sj[i] * sj[j];
+                        }
+                        __syncthreads();
+                        { double *tp = s.sigma; s.sigma = s.sigma_new; s.sigma_new = tp; }
+                        if (need_sq) {   // reads the UPDATED row j1 (the copy precedes the loop, :1166, 1191)
+                            const double *sn = s.sigma + j1 * M;
+                            for (int c = threadIdx.x; c < Kc; c += T) {
+                                double z = 0;
+                                for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sn[j], z);
+                                s.S_in[c] += z * z * kappa;
+                                s.Q_in[c] += mujj * kappa * z;
+                            }
+                            if (threadIdx.x == 0) b.flops += 2.0 * Kc * (double)M;
+                        }
+                    } else if (selected == ACT_ADD) {                                 // ActionAdd*, :830-1003
+                        const int n_used = M - 1;
+                        if (n_used + 1 > cap - 1) { b.status |= ST_CAP; selected = ACT_TERM; }
+                        else {
+                            {
+                                Cand<EPIS> cd(nu, K);
+                                const double sc_nu = scale[nu], isc = 1 / sc_nu;
+                                for (int h = threadIdx.x; h < N; h += T) {
+                                    const double x = cd.at(X + (size_t)h * K);
+                                    s.phinew[h] = EPIS ? x / sc_nu : x * isc;         // NeFull.c:253-262 vs NEmainEff.c:643-646
+                                }
+                            }
+                            __syncthreads();
+                            const int grow_new = s.grow[M];
+                            if (need_sq) {
+                                contract<EPIS>(X, N, K, Kc, 1,
+                                    [&](int) -> const double * { return s.phinew; },
+                                    [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, sV, s.w1);
+                            }
+                            {   // tmp = PHI' (w o phi_new), one warp per active column
+                                const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+                                for (int i = wid; i < M; i += nw) {
+                                    const double *p = s.phi + (size_t)i * N;
+                                    double z = 0;
+                                    for (int h = lane; h < N; h += 32) z = fma(p[h], s.w1[h] * s.phinew[h], z);
+                                    z = warp_sum(z);
+                                    if (lane == 0) s.tmp[i] = z;
+                                }
+                            }
+                            __syncthreads();
+                            for (int i = threadIdx.x; i < M; i += T) {
+                                double z = 0;
+                                for (int j = 0; j < M; j++) z = fma(s.sigma[i * M + j], s.tmp[j], z);
+                                s.u[i] = z;
+                            }
+                            for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)M * N + h] = s.phinew[h];
+                            const double s_ii = 1.0 / (new_alpha + s.S_in[nu]);
+                            const double mu_i = s_ii * s.Q_in[nu];
+                            __syncthreads();
+                            if (threadIdx.x == 0) { s.alpha[n_used] = new_alpha; s.mu[M] = mu_i; }
+                            for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mu_i * s.u[i];
+                            const int M1 = M + 1;
+                            for (int idx = threadIdx.x; idx < M1 * M1; idx += T) {
+                                const int j = idx / M1, i = idx - j * M1;
+                                double val;
+                                if (i < M && j < M) val = s.sigma[j * M + i] + (s_ii * s.u[i]) * s.u[j];
+                                else if (i == M && j == M) val = s_ii;
+                                else val = -s_ii * s.u[i < M ? i : j];
+                                s.sigma_new[idx] = val;
+                            }
+                            if (need_sq) {
+                                for (int c = threadIdx.x; c < Kc; c += T) {
+                                    double z = 0;
+                                    for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], s.u[j], z);
+                                    const double mci = s.G[(size_t)grow_new * Kc + c] - z;
+                                    s.S_in[c] -= mci * mci * s_ii;
+                                    s.Q_in[c] -= mu_i * mci;
+                                }
+                            }
+                            __syncthreads();
+                            if (threadIdx.x == 0) {
+                                s.used[n_used] = nu + 1;
+                                s.amap[nu] = n_used;
+                                const int p = s.upos[nu], nun = b.n_unused - 1;
+                                if (p < nun) { const int lastc = s.unused[nun] - 1; s.unused[p] = lastc + 1; s.upos[lastc] = p; }
+                                if (need_sq) b.flops += 2.0 * N * (double)Kc + 2.0 * Kc * (double)M;
+                            }
+                            { double *tp = s.sigma; s.sigma = s.sigma_new; s.sigma_new = tp; }
+                            b.n_unused--;
+                            b.M = M + 1;
+                        }
+                    } else if (selected == ACT_DEL) {                                 // ActionDel*, :1010-1121
+                        const int j1 = jj + 1, lastj = M - 1;
+                        const double *sj = s.sigma + j1 * M;
+                        const double sjj = sj[j1];
+                        const double mujj = s.mu[j1];
+                        const double al_last = s.alpha[lastj - 1];
+                        __syncthreads();
+                        for (int i = threadIdx.x; i < M; i += T) s.mu[i] = s.mu[i] - mujj * sj[i] / sjj;
+                        if (need_sq) {
+                            for (int c = threadIdx.x; c < Kc; c += T) {
+                                double z = 0;
+                                for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sj[j], z);
+                                s.S_in[c] += z * z / sjj;
+                                s.Q_in[c] += z * mujj / sjj;
+                            }
+                            if (threadIdx.x == 0) b.flops += 2.0 * Kc * (double)M;
+                        }
+                        for (int idx = threadIdx.x; idx < lastj * lastj; idx += T) {
+                            const int j = idx / lastj, i = idx - j * lastj;
+                            const int si = (i == j1) ? lastj : i, sjx = (j == j1) ? lastj : j;
+                            s.sigma_new[idx] = EPIS ? s.sigma[sjx * M + si] - sj[si] / sjj * sj[sjx]      // NeFull.c:1612
+                                                    : s.sigma[sjx * M + si] - sj[si] * sj[sjx] / sjj;     // NEmainEff.c:1069
+                        }
+                        if (j1 != lastj)
+                            for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)j1 * N + h] = s.phi[(size_t)lastj * N + h];
+                        __syncthreads();
+                        if (threadIdx.x == 0) {
+                            if (j1 != lastj) {
+                                s.alpha[jj] = al_last;
+                                s.mu[j1] = s.mu[lastj];
+                                const int gr = s.grow[j1]; s.grow[j1] = s.grow[lastj]; s.grow[lastj] = gr;
+                            }
+                            const int moved = s.used[lastj - 1];
+                            s.used[jj] = moved;
+                            s.amap[nu] = -1;
+                            if (jj != lastj - 1) s.amap[moved - 1] = jj;
+                            s.unused[b.n_unused] = nu + 1; s.upos[nu] = b.n_unused;
+                        }
+                        { double *tp = s.sigma; s.sigma = s.sigma_new; s.sigma_new = tp; }
+                        b.n_unused++;
+                        b.M = M - 1;
+                        if (nu + 1 == initial) ini_removed = 1;                       // :744
+                    }
+                    __syncthreads();
+                    if (!need_sq) binom_full_stat<EPIS>(P, F, s, b, sV, sc);          // after the last action of the block (:749-762)
+                }
+            }
+            if (selected == ACT_TERM && ini_removed) last = 1;
+            if ((i_iter == it_max && b.M == 2) || i_iter > it_max) last = 1;
+            if (i_iter == it_max) selected = ACT_TERM;
+            {   // global log-likelihood and its relative change (:782-801)
+                const int M = b.M;
+                double ll = 0;
+                for (int h = threadIdx.x; h < N; h += T) {
+                    double z = 0;
+                    for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * N + h], s.mu[j], z);
+                    const double ez = exp(z);
+                    ll += t[h] * log(ez / (1 + ez)) + (1 - t[h]) * log(1 / (1 + ez));
+                }
+                loglik = block_sum(ll, sc);
+                const double dL = fabs((loglik - logl0) / logl0);
+                if (dL < 1e-3) selected = ACT_TERM;
+            }
+        }
+        {
+            const int M = b.M;
+            vk = 0;
+            if (!EPIS) { for (int i = 0; i < M; i++) vk += fabs(s.alpha[i]); }        // dasum over m entries, one of them stale (:340)
+            else { for (int i = 0; i < M - 1; i++) vk += s.alpha[i]; }                // NeFull.c:138-139
+            err = fabs(vk - vk0) / M;
+        }
     }
+    if (iter >= 100) b.status |= ST_ITER_MAX;
+
+    // ---------------- hold-out score (R/GetModelError.R:34-57) ----------------
+    const int M = b.M;
+    __syncthreads();
+    for (int i = 1 + threadIdx.x; i < M; i += T) s.tmp[i] = s.mu[i] / scale[s.used[i - 1] - 1];
+    __syncthreads();
+    int nsel = 0;
+    for (int i = 1; i < M; i++) nsel += s.tmp[i] != 0;
+    double ll = 0;
+    if (nsel > 0) {
+        const double mu0 = s.mu[0];
+        for (int h = threadIdx.x; h < F.nte; h += T) {
+            const double *xr = F.Xte + (size_t)h * K;
+            double pred = 0;
+            for (int i = 1; i < M; i++) {
+                const double wgt = s.tmp[i];
+                if (wgt != 0) { Cand<EPIS> cd(s.used[i - 1] - 1, K); pred = fma(cd.at(xr), wgt, pred); }
+            }
+            double od = exp(mu0 + pred);
+            if (od > 1e10) od = 1e5;
+            if (od < 1e-10) od = 1e-5;
+            ll += F.yte[h] * log(od / (1 + od)) + (1 - F.yte[h]) * log(1 / (1 + od));
+        }
+        ll = block_sum(ll, sc) / F.nte;
+    }
+    if (!isfinite(ll)) b.status |= ST_NONFINITE;
+    if (threadIdx.x == 0) {
+        const int o = task.out_index;
+        if (out.fold_err) out.fold_err[o] = ll;
+        if (out.status) out.status[o] = b.status;
+        if (out.n_selected) out.n_selected[o] = nsel;
+        if (out.n_iter) out.n_iter[o] = iter;
+        if (out.flops) atomicAdd(out.flops, b.flops);
+        if (out.m_out) {
+            out.m_out[0] = M - 1;
+            double wd = 0;
+            for (int i = 0; i < M; i++) {
+                double z = 0;
+                for (int j = 0; j < M; j++) z += s.mu[j] * s.H[i * M + j];
+                wd += z * s.mu[i];
+            }
+            for (int i = 1; i < M; i++) {
+                const int c = s.used[i - 1] - 1;
+                out.used_out[i - 1] = s.used[i - 1];
+                out.beta_out[i - 1] = s.mu[i] / scale[c];
+                out.var_out[i - 1] = s.sigma[i * M + i] / (scale[c] * scale[c]);
+            }
+            out.scalars_out[0] = wd; out.scalars_out[1] = s.mu[0]; out.scalars_out[2] = s.sigma[0]; out.scalars_out[3] = loglik;
+        }
+    }
+    __syncthreads();
 }
+
 }  // namespace pareben

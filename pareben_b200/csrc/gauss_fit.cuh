@@ -32,8 +32,8 @@ constexpr int TH = 64;    // rows per shared-memory tile
 
 template <bool EPIS, class ColPtr, class Store>
 __device__ inline void contract(const double *__restrict__ X, int N, int K, int Kc, int R, ColPtr colptr,
-                                Store store, double *sV /* TH*RC doubles */)
-{
+                                Store store, double *sV /* TH*RC doubles */, const double *rw = nullptr)
+{   // rw (optional): per-row weights multiplied into V while staging (IRLS weights of the binomial fit)
     const int T = blockDim.x;
     for (int c0 = 0; c0 < Kc; c0 += T) {
         const int c = c0 + threadIdx.x;
@@ -50,7 +50,7 @@ __device__ inline void contract(const double *__restrict__ X, int N, int K, int 
                 for (int idx = threadIdx.x; idx < TH * RC; idx += T) {
                     const int r = idx / TH, h = idx - r * TH;      // consecutive threads -> consecutive rows (coalesced)
                     double v = 0.0;
-                    if (r < nr && h < nh) v = colptr(r0 + r)[h0 + h];
+                    if (r < nr && h < nh) { v = colptr(r0 + r)[h0 + h]; if (rw) v *= rw[h0 + h]; }
                     sV[h * RC + r] = v;
                 }
                 __syncthreads();
@@ -221,16 +221,16 @@ __device__ inline bool final_update(Slab &s, GaussState &g, int N, const Scratch
 
 struct Decision { double best; int nu; int any_delete; };
 
-template <bool EPIS>
-__device__ inline Decision delta_ml(Slab &s, GaussState &g, const Variant &v, int N, int Kc, double lambda,
+// M = number of active effects (the binomial intercept is not counted).
+template <bool EPIS, bool BINOM>
+__device__ inline Decision delta_ml(Slab &s, int M, int N, int Kc, double lambda,
                                     double alpha_en, double residual, double var_y, int iter, int i_iter,
                                     const Scratch &sc)
-{   // fEBDeltaML* (MainEff.c:1372-1582; NeFull2.c:1227-1404)
+{   // fEBDeltaML* (MainEff.c:1372-1582; NeFull2.c:1227-1404; NEmainEff.c:2063-2238; NeFull.c:1775-1950)
     const double l1 = lambda * alpha_en, l2 = lambda * (1 - alpha_en);
-    const int M = g.M;
     int prio_add = 0, prio_del = 0;
     if (M < 10) { prio_add = 1; prio_del = 0; }
-    if (M > 100 || (!EPIS && M >= N) || residual <= var_y * 0.1) { prio_add = 0; prio_del = 1; }
+    if (M > 100 || (!EPIS && M >= N) || (!BINOM && residual <= var_y * 0.1)) { prio_add = 0; prio_del = 1; }
     double lbest = 0; int lkey = 0x7fffffff, larg = 0;
     int f_add = 0, f_del = 0;
     for (int c = threadIdx.x; c < Kc; c += blockDim.x) {
@@ -255,7 +255,7 @@ __device__ inline Decision delta_ml(Slab &s, GaussState &g, const Variant &v, in
                 } else {
                     act = ACT_ADD;
                     d_ml = L;
-                    if (!EPIS) f_add = 1;          // only the main-effect file ever sets anyToAdd (:1484)
+                    if (!EPIS && !BINOM) f_add = 1;   // only the Gaussian main-effect file ever sets anyToAdd (:1484)
                 }
             }
         } else if (i >= 0 && M > 1) {
@@ -283,7 +283,7 @@ __device__ inline Decision delta_ml(Slab &s, GaussState &g, const Variant &v, in
         }
         rescan = true;
     }
-    if (!EPIS && ((!any_add && iter == 1 && i_iter < 10) || (!any_add && residual >= var_y * 0.95))) {   // :1557-1577
+    if (!EPIS && !BINOM && ((!any_add && iter == 1 && i_iter < 10) || (!any_add && residual >= var_y * 0.95))) {   // :1557-1577
         for (int c = threadIdx.x; c < Kc; c += blockDim.x) if (s.action[c] == ACT_DEL) s.dml[c] = 0;
         rescan = true;
     }
@@ -369,7 +369,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
         const int it_max = iter == 1 ? 10 : 100;
         while (!last) {
             i_iter++;
-            Decision d = delta_ml<EPIS>(s, g, v, N, Kc, lambda, alpha_en, residvar, var_y, iter, i_iter, sc);
+            Decision d = delta_ml<EPIS, false>(s, g.M, N, Kc, lambda, alpha_en, residvar, var_y, iter, i_iter, sc);
             int nu = d.nu, worthwhile;
             if (selected == ACT_TERM && !ini_removed && g.M > 1) nu = -1;          // :426-430
             if (nu == -1 && ini_removed) { worthwhile = 0; selected = ACT_TERM; }
@@ -436,8 +436,12 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             // new normalised column (on the fly for pairs)
                             {
                                 Cand<EPIS> cd(nu, K);
-                                const double isc = 1 / scale[nu];
-                                for (int h = threadIdx.x; h < N; h += T) s.phinew[h] = cd.at(X + (size_t)h * K) * isc;
+                                const double sc_nu = scale[nu], isc = 1 / sc_nu;
+                                const bool pair = cd.i != cd.j;     // pairs are divided, main effects scaled by 1/s (NeFull2.c:277-290)
+                                for (int h = threadIdx.x; h < N; h += T) {
+                                    const double x = cd.at(X + (size_t)h * K);
+                                    s.phinew[h] = pair ? x / sc_nu : x * isc;
+                                }
                             }
                             __syncthreads();
                             const int grow_new = s.grow[M];

@@ -1,8 +1,16 @@
 #!/bin/bash
-# one gpurun call: build check, gpu tests, probe
-set -x
+# one gpurun call: build check, gpu tests, bench, ncu launch list + one full capture
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { tail -20 gpurun_out/build.log; exit 1; }
-nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -30
-timeout 600 python scripts/gpu_probe.py 2>&1 | tail -20
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv,noheader
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+if [ "$1" == "ncu" ]; then
+  timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/plain_bench.log 2>&1 &&
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_launches.log 2>&1
+  echo "launch list rc=$?"
+  timeout 300 python scripts/profile_case.py binomial 296 > gpurun_out/plain_profile.log 2>&1 &&
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:eben_fit -s 1 -c 1 -o gpurun_out/prof_binom python scripts/profile_case.py binomial 296 > gpurun_out/ncu_full.log 2>&1
+  echo "full capture rc=$?"; tail -3 gpurun_out/ncu_full.log; cat gpurun_out/plain_profile.log
+fi

@@ -154,3 +154,47 @@ def test_edge_cases(pb):
     assert np.all(np.isfinite(err))
     err2, _, _ = pb.cv_grid(X[:, :1], y, folds, 3, np.ones(2), np.array([1.0, 0.01]))   # K = 1
     assert err2.shape == (2, 3) and np.all(np.isfinite(err2))
+
+
+def test_config2_binomial_full_grid(pb, bundled):
+    """BASELINE config 2: bundled 500 x 481 logistic data, 5 folds, all 2,000 fits."""
+    g = golden("config2_binomial.npz")
+    X, y = bundled["BASISbinomial"].astype(float), bundled["yBinomial"].astype(float)
+    err, st, ns = pb.cv_grid(X, y, g["fold_id"], 5, g["grid_alpha"], g["grid_lambda"], prior="binomial")
+    assert np.all(st == 0)
+    diff = ns != g["n_selected"]
+    assert diff.sum() == 0, f"{diff.sum()} of 2000 fits with a different support size"
+    assert _rel(err, g["fold_err"]) < RTOL
+    out = pb.CrossValidate(X, y, 5, prior="binomial")
+    assert abs(out["alpha.optimal"] - float(g["alpha_optimal"])) < 1e-15
+    assert abs(out["lambda.optimal"] - float(g["lambda_optimal"])) <= 1e-13 * float(g["lambda_optimal"])
+    assert _rel(out["Results.Summary"]["Likelihood"], g["summary_likelihood"]) < RTOL
+    loc = pb.CrossValidate(X, y, 5, foldId=g["fold_id"], prior="binomial", search="local")
+    want = R.local_search_replay(g["grid_alpha"], g["grid_lambda"], -g["fold_err"])
+    assert loc["alpha.optimal"] == want[1] and abs(loc["lambda.optimal"] - want[2]) <= 1e-13 * want[2]
+    assert np.allclose(loc["fullCV"], want[3], rtol=1e-8, atol=0)
+
+
+def test_binomial_epis_slice(pb, bundled):
+    g = golden("binom_epis_slice.npz")
+    X, y = bundled["BASISbinomial"][::4, :20].astype(float), bundled["yBinomial"][::4].astype(float)
+    rows = g["rows"]
+    err, st, ns = pb.cv_grid(X, y, g["fold_id"], 3, g["grid_alpha"][rows], g["grid_lambda"][rows], epis=True, prior="binomial")
+    assert np.array_equal(ns, g["n_selected"])
+    assert np.max(np.abs(err - g["fold_err"]) / np.maximum(np.abs(g["fold_err"]), 1e-12)) < RTOL
+
+
+def test_binomial_final_model_live(pb, bundled):
+    lib = R.fit_lib(R.available_kind())
+    X, y = bundled["BASISbinomial"][:, :120].astype(float), bundled["yBinomial"].astype(float)
+    rng = np.random.default_rng(5)
+    rows = rng.permutation(500)[:300]
+    X, y = X[rows], y[rows]
+    for lam, a in ((0.5, 1.0), (0.05, 0.5)):
+        want = R.eb_elastic_net_binomial(X, y, lam, a, False, lib)
+        got = pb.EBelasticNet_Binomial(X, y, lam, a)
+        assert got["weight"].shape == want.weight.shape
+        assert np.array_equal(got["weight"][:, :2], want.weight[:, :2])
+        assert np.allclose(got["weight"][:, 2:4], want.weight[:, 2:4], rtol=1e-7, atol=1e-12)
+        assert np.allclose(got["Intercept"], want.intercept, rtol=1e-7)
+        assert abs(got["logLikelihood"] - want.log_likelihood) <= 1e-8 * abs(want.log_likelihood)

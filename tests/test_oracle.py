@@ -129,3 +129,42 @@ def test_port_vs_reference_live_random(built):
             assert np.allclose(f1.weight[:, :4], f2.weight[:, :4], rtol=1e-8, atol=1e-12)
             assert abs(f1.intercept[0] - f2.intercept[0]) < 1e-9 * abs(f1.intercept[0])
             assert abs(f1.wald - f2.wald) <= 1e-8 * max(1.0, abs(f1.wald))
+
+
+def _port_table_binom(X, y, n_folds, epis, g, rows_idx):
+    lib = R.fit_lib("port")
+    out = np.zeros((len(rows_idx), n_folds)); ns = np.zeros((len(rows_idx), n_folds), dtype=np.int32)
+    for i, ri in enumerate(rows_idx):
+        r = g["rows"][ri]
+        for f in range(1, n_folds + 1):
+            e, fit = R.fit_one(X, y, g["fold_id"], f, g["grid_lambda"][r], g["grid_alpha"][r], epis, "binomial", lib)
+            out[i, f - 1] = e
+            ns[i, f - 1] = 0 if fit.weight[0, 0] == 0 else fit.weight.shape[0]
+    return out, ns
+
+
+def test_port_binomial_config2_rows(bundled, built):
+    """Config 2 (500 x 481 logistic, 5 folds): anchors from SURVEY D.2 and a sample of grid rows."""
+    g = golden("config2_binomial.npz")
+    X, y = bundled["BASISbinomial"].astype(float), bundled["yBinomial"].astype(float)
+    assert abs(g["grid_lambda"][0] - 4.9018946774254) < 1e-12
+    assert list(g["fold_id"][:12]) == [4, 2, 4, 3, 1, 4, 5, 1, 2, 2, 1, 5]
+    assert abs(float(g["alpha_optimal"]) - 0.2) < 1e-12 and abs(float(g["lambda_optimal"]) - 0.0145897612898799) < 1e-14
+    assert abs(g["summary_likelihood"].min() - 0.338311255040) < 1e-10
+    assert np.allclose(g["fold_err"][0], [-0.60967424, -0.63577811, -0.62685061, -0.61303727, -0.60829047], atol=1e-8)
+    assert np.allclose(g["fold_err"][399], [-0.32703985, -0.28302331, -0.42632759, -0.26404669, -0.42251053], atol=1e-8)
+    assert list(g["n_selected"][399]) == [39, 47, 46, 42, 43]
+    idx = [0, 45, 130, 399]
+    err, ns = _port_table_binom(X, y, 5, False, g, idx)
+    assert np.array_equal(ns, g["n_selected"][idx])
+    assert np.max(np.abs(err - g["fold_err"][idx]) / np.abs(g["fold_err"][idx])) < 1e-9
+
+
+def test_port_binomial_epis_slice(bundled, built):
+    g = golden("binom_epis_slice.npz")
+    X, y = bundled["BASISbinomial"][::4, :20].astype(float), bundled["yBinomial"][::4].astype(float)
+    idx = list(range(0, len(g["rows"]), 3))
+    err, ns = _port_table_binom(X, y, 3, True, g, idx)
+    assert np.array_equal(ns, g["n_selected"][idx])
+    ref = g["fold_err"][idx]
+    assert np.max(np.abs(err - ref) / np.maximum(np.abs(ref), 1e-12)) < 1e-9
