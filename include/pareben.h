@@ -60,6 +60,10 @@ int pareben_problem_create(pareben_problem **out, int device, const double *basi
                            const double *target, const int *fold_id, int n_folds, int epis, int prior);
 void pareben_problem_destroy(pareben_problem *p);
 
+/* The library keeps one per-device work buffer alive between calls (allocating several GB per
+ * CrossValidate would dominate small problems); this releases it. */
+void pareben_release_cache(void);
+
 /* Run n_fits independent EBEN fits in one batched launch.  Fit i trains on the rows whose fold
  * label differs from fold[i] (1-based; 0 = all rows) with hyper-parameters (alpha[i], lambda[i])
  * and is scored on the held-out rows as R/GetModelError.R does: Gaussian -> sum of squared

@@ -25,6 +25,7 @@ SIGNATURES = {
     "pareben_problem_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, _dp, ctypes.c_int, ctypes.c_int, _dp, _ip,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "pareben_problem_destroy": (None, [_vp]),
+    "pareben_release_cache": (None, []),
     "pareben_run_fits": (ctypes.c_int, [_vp, ctypes.c_int, _ip, _dp, _dp, _dp, _ip, _ip, _ip]),
     "pareben_cv_grid": (ctypes.c_int, [_dp, ctypes.c_int, ctypes.c_int, _dp, _ip, ctypes.c_int, _dp, _dp, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _ip, _ip]),

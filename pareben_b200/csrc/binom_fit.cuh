@@ -73,29 +73,37 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
         block_sum2(g0, h0, sc);
         if (threadIdx.x == 0) { g[0] = g0; s.H[0] = h0; }
         __syncthreads();
-        // gradient, first row/column, and the upper triangle of PHI' B PHI (+ diag(alpha)); one warp per entry
-        const int m1 = M - 1, npair = m1 * (m1 + 1) / 2;
-        for (int p = wid; p < m1 + npair; p += nw) {
-            if (p < m1) {
-                const int j = p + 1;
-                const double *ph = s.phi + (size_t)j * N;
-                double gj = 0, hj = 0;
-                for (int h = lane; h < N; h += 32) { gj = fma(ph[h], e[h], gj); hj = fma(w[h], ph[h], hj); }
-                gj = warp_sum(gj); hj = warp_sum(hj);
-                if (lane == 0) { g[j] = gj - s.alpha[j - 1] * s.mu[j]; s.H[j] = hj; s.H[j * M] = hj; }
-            } else {
-                const int q = p - m1;
-                int k = (int)floor((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
-                while ((k + 1) * (k + 2) / 2 <= q) k++;
-                while (k * (k + 1) / 2 > q) k--;
-                const int j = q - k * (k + 1) / 2;            // j <= k, both 0-based over effects
-                const double *a = s.phi + (size_t)(j + 1) * N, *c = s.phi + (size_t)(k + 1) * N;
-                double z = 0;
-                for (int h = lane; h < N; h += 32) z = fma(a[h] * w[h], c[h], z);
-                z = warp_sum(z);
-                if (lane == 0) {
-                    if (j == k) z += s.alpha[k];
-                    s.H[(k + 1) * M + (j + 1)] = z; s.H[(j + 1) * M + (k + 1)] = z;
+        // gradient, first row/column, and the upper triangle of PHI' B PHI (+ diag(alpha)).
+        // One warp per (j, block of 8 columns k >= j): lanes stride the rows, phi_j[h] w[h] is
+        // formed once and reused for the 8 products, as the reference's (phi_j * beta) * phi_k order.
+        const int m1 = M - 1;
+        for (int j = 1 + wid; j < M; j += nw) {
+            const double *ph = s.phi + (size_t)j * N;
+            double gj = 0, hj = 0;
+            for (int h = lane; h < N; h += 32) { gj = fma(ph[h], e[h], gj); hj = fma(w[h], ph[h], hj); }
+            gj = warp_sum(gj); hj = warp_sum(hj);
+            if (lane == 0) { g[j] = gj - s.alpha[j - 1] * s.mu[j]; s.H[j] = hj; s.H[j * M] = hj; }
+        }
+        const int kb = (m1 + 7) / 8;                 // column blocks
+        for (int item = wid; item < m1 * kb; item += nw) {
+            const int j = item / kb + 1, k0 = (item - (j - 1) * kb) * 8 + 1;
+            if (k0 + 7 < j) continue;                // block entirely below the diagonal
+            const double *a = s.phi + (size_t)j * N;
+            double z[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) z[q] = 0.0;
+            for (int h = lane; h < N; h += 32) {
+                const double aw = a[h] * w[h];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { const int k = min(k0 + q, m1); z[q] = fma(aw, s.phi[(size_t)k * N + h], z[q]); }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const double zz = warp_sum(z[q]);
+                const int k = k0 + q;
+                if (lane == 0 && k <= m1 && k >= j) {
+                    const double val = (j == k) ? zz + s.alpha[k - 1] : zz;
+                    s.H[k * M + j] = val; s.H[j * M + k] = val;
                 }
             }
         }
@@ -150,27 +158,22 @@ __device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab
         e[h] = t[h] - y;
     }
     __syncthreads();
-    // G[p][c] = sum_h x_c[h] phi_p[h] w[h] / s_c   (BPvector, :1693-1702) -- kept as the action cache
-    contract<EPIS>(X, N, K, Kc, M,
-        [&](int r) -> const double * { return s.phi + (size_t)r * N; },
-        [&](int r, int c, double acc) { s.G[(size_t)s.grow[r] * Kc + c] = acc / scale[c]; }, sV, w);
-    for (int c = threadIdx.x; c < Kc; c += T) {
-        Cand<EPIS> cd(c, K);
-        double bb = 0, ze = 0;
-        const double *xr = X;
-        for (int h = 0; h < N; h++, xr += K) { const double x = cd.at(xr); bb = fma(w[h], x * x, bb); ze = fma(x, e[h], ze); }
-        double quad = 0;
-        for (int p = 0; p < M; p++) {
-            const double *sp = s.sigma + p * M;
-            double z = 0;
-            for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sp[j], z);
-            quad = fma(z, s.G[(size_t)s.grow[p] * Kc + c], quad);
-        }
+    // One pass over the shared training matrix gives, per candidate c,
+    //   r = 0      bb = sum_h w[h] x_c[h]^2             (BBsquare, :1728-1729)
+    //   r = 1      ze = sum_h x_c[h] e[h]               (tempZE,  :1731-1732)
+    //   r = 2+p    G[p][c] = sum_h x_c[h] phi_p[h] w[h] / s_c   (BPvector, :1693-1702) -- kept as the action cache
+    contract_x<EPIS>(F, K, Kc, M + 2,
+        [&](int r, int h) { return r == 0 ? w[h] : (r == 1 ? e[h] : s.phi[(size_t)(r - 2) * N + h] * w[h]); },
+        [&](int r, int c, double acc) {
+            if (r == 0) s.S_in[c] = acc;
+            else if (r == 1) s.Q_in[c] = acc;
+            else s.G[(size_t)s.grow[r - 2] * Kc + c] = acc / scale[c];
+        }, sV, true);
+    quad_forms(s, s.sigma, s.sigma_new, M, Kc, nullptr, [&](int c, double quad, double) {
         const double sc_c = scale[c];
-        s.S_in[c] = bb / (sc_c * sc_c) - quad;
-        s.Q_in[c] = ze / sc_c;
-    }
-    __syncthreads();
+        s.S_in[c] = s.S_in[c] / (sc_c * sc_c) - quad;
+        s.Q_in[c] = s.Q_in[c] / sc_c;
+    });
     if (threadIdx.x == 0) b.flops += 2.0 * N * (double)Kc * (M + 2) + (double)Kc * (2.0 * M * M + M);
     refresh_out(s, M - 1, Kc);
 }
@@ -319,9 +322,9 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                             __syncthreads();
                             const int grow_new = s.grow[M];
                             if (need_sq) {
-                                contract<EPIS>(X, N, K, Kc, 1,
-                                    [&](int) -> const double * { return s.phinew; },
-                                    [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, sV, s.w1);
+                                contract_x<EPIS>(F, K, Kc, 1,
+                                    [&](int, int h) { return s.phinew[h] * s.w1[h]; },
+                                    [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, sV);
                             }
                             {   // tmp = PHI' (w o phi_new), one warp per active column
                                 const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;

@@ -32,6 +32,7 @@ struct Variant {
 
 struct FoldData {
     const double *Xtr;       // [ntr][K] row-major training rows
+    const int8_t *Xtr8;      // same matrix as int8 when every entry is a small integer (genotype codes), else null
     const double *ytr;       // [ntr]
     const double *Xte;       // [nte][K] row-major held-out rows
     const double *yte;       // [nte]
@@ -68,9 +69,14 @@ struct Slab {
     int *unused, *upos, *amap, *action, *block;   // Kc each
 };
 
+// Each of the three cap x cap matrices is over-allocated to cap x (cap + 8), rounded to a multiple
+// of 4 doubles, so that either SIGMA buffer can hold the padded copy quad_forms() reads with
+// 32-byte loads.
+__host__ __device__ inline size_t sig_elems(int cap) { return (((size_t)cap * (cap + 8)) + 3) & ~(size_t)3; }
+
 __host__ __device__ inline size_t slab_doubles(int cap, int nmax, int Kc)
 {
-    return (size_t)3 * cap * cap + (size_t)nmax * cap + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
+    return 3 * sig_elems(cap) + (size_t)nmax * cap + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
            (size_t)6 * (cap + 1);
 }
 __host__ __device__ inline size_t slab_ints(int cap, int Kc) { return (size_t)2 * cap + (size_t)5 * Kc; }
@@ -84,9 +90,9 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
 {
     Slab s;
     double *d = reinterpret_cast<double *>(base);
-    s.sigma = d; d += (size_t)cap * cap;
-    s.sigma_new = d; d += (size_t)cap * cap;
-    s.H = d; d += (size_t)cap * cap;
+    s.sigma = d; d += sig_elems(cap);
+    s.sigma_new = d; d += sig_elems(cap);
+    s.H = d; d += sig_elems(cap);
     s.phi = d; d += (size_t)nmax * cap;
     s.G = d; d += (size_t)cap * Kc;
     s.xt = d; d += Kc; s.S_in = d; d += Kc; s.Q_in = d; d += Kc; s.S_out = d; d += Kc; s.Q_out = d; d += Kc;
@@ -208,6 +214,11 @@ struct Cand {
     {
         if (EPIS) return i == j ? Xrow[i] : Xrow[i] * Xrow[j];
         return Xrow[i];
+    }
+    __device__ inline double at(const int8_t *Xrow) const      // exact: |x| <= 127, products <= 2^14
+    {
+        if (EPIS) return i == j ? (double)Xrow[i] : (double)((int)Xrow[i] * (int)Xrow[j]);
+        return (double)Xrow[i];
     }
 };
 

@@ -24,16 +24,22 @@ struct GaussState {
 
 // ---- contraction: out(r, c) = sum_h x_c[h] * V_r[h]  for r in [0,R), c in [0,Kc) -------------
 // Thread-per-candidate, RC right-hand sides per pass kept in registers; the V tile is staged in
-// shared memory ([TH rows][RC]) so every X element fetched from L2 feeds RC FMAs.
+// shared memory ([TH rows][RC]) so every X element fetched from L2/L1 feeds RC FMAs.  X loads run
+// PF rows ahead of the FMAs (software prefetch) because with ~16 warps per SM it is load latency,
+// not the FP64 pipe, that limits this loop.
 // Summation over rows is sequential in h for every (r, c): identical arithmetic for identical
 // columns, so exact duplicates tie exactly.
+//   colval(r, h)  value of right-hand side r at row h (the caller folds any row weight in)
+//   sq_first      when true, right-hand side 0 is contracted with x^2 instead of x
+//                 (the binomial sum_h w[h] x^2, NEmainEff.c:1728-1729)
 constexpr int RC = 8;     // right-hand sides per register tile
-constexpr int TH = 64;    // rows per shared-memory tile
+constexpr int TH = 128;   // rows per shared-memory tile
+constexpr int PF = 8;     // rows of X prefetched per group
 
-template <bool EPIS, class ColPtr, class Store>
-__device__ inline void contract(const double *__restrict__ X, int N, int K, int Kc, int R, ColPtr colptr,
-                                Store store, double *sV /* TH*RC doubles */, const double *rw = nullptr)
-{   // rw (optional): per-row weights multiplied into V while staging (IRLS weights of the binomial fit)
+template <bool EPIS, class XT, class ColVal, class Store>
+__device__ inline void contract(const XT *__restrict__ X, int N, int K, int Kc, int R, ColVal colval,
+                                Store store, double *sV /* TH*RC doubles */, bool sq_first = false)
+{
     const int T = blockDim.x;
     for (int c0 = 0; c0 < Kc; c0 += T) {
         const int c = c0 + threadIdx.x;
@@ -41,29 +47,40 @@ __device__ inline void contract(const double *__restrict__ X, int N, int K, int 
         Cand<EPIS> cd(live ? c : 0, K);
         for (int r0 = 0; r0 < R; r0 += RC) {
             const int nr = min(RC, R - r0);
+            const bool sq = sq_first && r0 == 0;
             double acc[RC];
 #pragma unroll
             for (int r = 0; r < RC; r++) acc[r] = 0.0;
             for (int h0 = 0; h0 < N; h0 += TH) {
                 const int nh = min(TH, N - h0);
+                const int nh8 = (nh + PF - 1) / PF * PF;          // rows past nh are staged as zeros
                 __syncthreads();
-                for (int idx = threadIdx.x; idx < TH * RC; idx += T) {
-                    const int r = idx / TH, h = idx - r * TH;      // consecutive threads -> consecutive rows (coalesced)
-                    double v = 0.0;
-                    if (r < nr && h < nh) { v = colptr(r0 + r)[h0 + h]; if (rw) v *= rw[h0 + h]; }
-                    sV[h * RC + r] = v;
+                for (int idx = threadIdx.x; idx < nh8 * RC; idx += T) {
+                    const int r = idx / nh8, h = idx - r * nh8;    // consecutive threads -> consecutive rows (coalesced)
+                    sV[h * RC + r] = (r < nr && h < nh) ? colval(r0 + r, h0 + h) : 0.0;
                 }
                 __syncthreads();
                 if (live) {
-                    const double *xr = X + (size_t)h0 * K;
-                    for (int h = 0; h < nh; h++, xr += K) {
-                        const double x = cd.at(xr);
-                        const double4 *v4 = reinterpret_cast<const double4 *>(sV + h * RC);
-                        const double4 a = v4[0], b = v4[1];
-                        acc[0] = fma(x, a.x, acc[0]); acc[1] = fma(x, a.y, acc[1]);
-                        acc[2] = fma(x, a.z, acc[2]); acc[3] = fma(x, a.w, acc[3]);
-                        acc[4] = fma(x, b.x, acc[4]); acc[5] = fma(x, b.y, acc[5]);
-                        acc[6] = fma(x, b.z, acc[6]); acc[7] = fma(x, b.w, acc[7]);
+                    double xv[PF];
+#pragma unroll
+                    for (int i = 0; i < PF; i++) xv[i] = cd.at(X + (size_t)min(h0 + i, N - 1) * K);
+                    for (int hh = 0; hh < nh8; hh += PF) {
+                        double xn[PF];
+                        const int hb = h0 + hh + PF;
+#pragma unroll
+                        for (int i = 0; i < PF; i++) xn[i] = cd.at(X + (size_t)min(hb + i, N - 1) * K);   // next group in flight
+#pragma unroll
+                        for (int i = 0; i < PF; i++) {
+                            const double x = xv[i];
+                            const double4 *v4 = reinterpret_cast<const double4 *>(sV + (hh + i) * RC);
+                            const double4 a = v4[0], b = v4[1];
+                            acc[0] = fma(sq ? x * x : x, a.x, acc[0]); acc[1] = fma(x, a.y, acc[1]);
+                            acc[2] = fma(x, a.z, acc[2]); acc[3] = fma(x, a.w, acc[3]);
+                            acc[4] = fma(x, b.x, acc[4]); acc[5] = fma(x, b.y, acc[5]);
+                            acc[6] = fma(x, b.z, acc[6]); acc[7] = fma(x, b.w, acc[7]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < PF; i++) xv[i] = xn[i];
                     }
                 }
             }
@@ -72,6 +89,58 @@ __device__ inline void contract(const double *__restrict__ X, int N, int K, int 
                 for (int r = 0; r < RC; r++) if (r < nr) store(r0 + r, c, acc[r]);
             }
         }
+    }
+    __syncthreads();
+}
+
+// Dispatch on the storage type of the shared training matrix (int8 genotype codes when available).
+template <bool EPIS, class ColVal, class Store>
+__device__ inline void contract_x(const FoldData &F, int K, int Kc, int R, ColVal colval, Store store, double *sV,
+                                  bool sq_first = false)
+{
+    if (F.Xtr8) contract<EPIS, int8_t>(F.Xtr8, F.ntr, K, Kc, R, colval, store, sV, sq_first);
+    else contract<EPIS, double>(F.Xtr, F.ntr, K, Kc, R, colval, store, sV, sq_first);
+}
+
+// Quadratic forms of the candidate cache against the active-set inverse:
+//   quad[c] = g_c' SIGMA g_c,  lin[c] = g_c' v      with g_c = G[:, c]   (FullStat*, MainEff.c:1291-1316)
+// SIGMA is first copied to a padded layout (leading dimension ldp, multiple of 8, in `sigp`) so a
+// thread reads 8 consecutive entries of a row with two 32-byte loads; z_p accumulates over j in
+// ascending order and quad over p in ascending order, as the reference's loops do.
+template <class Emit>
+__device__ inline void quad_forms(const Slab &s, const double *sigma, double *sigp, int M, int Kc, const double *v,
+                                  Emit emit)
+{
+    const int T = blockDim.x;
+    const int ldp = (M + 7) & ~7;
+    for (int idx = threadIdx.x; idx < M * ldp; idx += T) {
+        const int j = idx / ldp, p = idx - j * ldp;
+        sigp[idx] = p < M ? sigma[p * M + j] : 0.0;           // sigp[j][p] = SIGMA(p, j)
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Kc; c += T) {
+        double quad = 0, lin = 0;
+        for (int p0 = 0; p0 < M; p0 += 8) {
+            double z[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) z[q] = 0.0;
+            for (int j = 0; j < M; j++) {
+                const double g = s.G[(size_t)s.grow[j] * Kc + c];
+                const double4 *row = reinterpret_cast<const double4 *>(sigp + (size_t)j * ldp + p0);
+                const double4 a = row[0], b = row[1];
+                z[0] = fma(g, a.x, z[0]); z[1] = fma(g, a.y, z[1]); z[2] = fma(g, a.z, z[2]); z[3] = fma(g, a.w, z[3]);
+                z[4] = fma(g, b.x, z[4]); z[5] = fma(g, b.y, z[5]); z[6] = fma(g, b.z, z[6]); z[7] = fma(g, b.w, z[7]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (p0 + q < M) {
+                    const double gp = s.G[(size_t)s.grow[p0 + q] * Kc + c];
+                    quad = fma(z[q], gp, quad);
+                    if (v) lin = fma(gp, v[p0 + q], lin);
+                }
+            }
+        }
+        emit(c, quad, lin);
     }
     __syncthreads();
 }
@@ -172,20 +241,11 @@ __device__ inline void full_stat(Slab &s, GaussState &g, int N, int Kc, bool fir
     posterior_mean(s, g, N);
     for (int i = 1 + threadIdx.x; i < M; i += blockDim.x) s.gamma[i] = 1.0 - s.sigma[i * M + i] * s.alpha[i];
     const double beta = g.beta;
-    for (int c = threadIdx.x; c < Kc; c += blockDim.x) {
-        double quad = 0, gm = 0;
-        for (int j = 0; j < M; j++) {
-            const double *sj = s.sigma + j * M;
-            double z = 0;
-            for (int p = 0; p < M; p++) z = fma(s.G[(size_t)s.grow[p] * Kc + c], sj[p], z);
-            const double gj = s.G[(size_t)s.grow[j] * Kc + c];
-            quad = fma(z, gj, quad);
-            gm = fma(gj, s.mu[j], gm);
-        }
+    __syncthreads();
+    quad_forms(s, s.sigma, s.sigma_new, M, Kc, s.mu, [&](int c, double quad, double gm) {
         s.S_in[c] = beta - beta * quad * beta;
         s.Q_in[c] = beta * (s.xt[c] - gm);
-    }
-    __syncthreads();
+    });
     if (threadIdx.x == 0) g.flops += (double)Kc * (2.0 * M * M + 2.0 * M);
     refresh_out(s, M, Kc);
 }
@@ -355,8 +415,8 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
         // candidate cache G = PHI'X/s and xt = X't/s  (CacheBP*, :1144-1201)
         {
             const int M = g.M;
-            contract<EPIS>(X, N, K, Kc, M + 1,
-                [&](int r) -> const double * { return r < M ? s.phi + (size_t)r * N : s.t; },
+            contract_x<EPIS>(F, K, Kc, M + 1,
+                [&](int r, int h) { return r < M ? s.phi[(size_t)r * N + h] : s.t[h]; },
                 [&](int r, int c, double acc) {
                     if (r < M) s.G[(size_t)s.grow[r] * Kc + c] = acc / scale[c];
                     else s.xt[c] = acc / scale[c];
@@ -445,8 +505,8 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             }
                             __syncthreads();
                             const int grow_new = s.grow[M];
-                            contract<EPIS>(X, N, K, Kc, 1,
-                                [&](int) -> const double * { return s.phinew; },
+                            contract_x<EPIS>(F, K, Kc, 1,
+                                [&](int, int h) { return s.phinew[h]; },
                                 [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, sV);
                             phi_dot(s.phi, N, M, s.phinew, s.tmp, g.beta);             // tmp = beta PHI' phi
                             for (int i = threadIdx.x; i < M; i += T) {

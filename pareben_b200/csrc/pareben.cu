@@ -9,6 +9,7 @@
 #include "binom_fit.cuh"
 
 #include <algorithm>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +23,13 @@ namespace {
 thread_local std::string g_err;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+// Per-device cache of the big per-block work slab: a CrossValidate call would otherwise pay a
+// multi-GB cudaMalloc/cudaFree every time.  One buffer per device is kept between calls and
+// released by pareben_release_cache() (or at process exit).
+struct SlabCache { void *ptr = nullptr; size_t bytes = 0; };
+SlabCache g_slab_cache[64];
+std::mutex g_cache_mu;
 
 #define CU(call)                                                                                  \
     do {                                                                                          \
@@ -57,6 +65,12 @@ __global__ void gather_vec_kernel(const double *__restrict__ y, const int *__res
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < nrows) out[r] = y[rows[r]];
+}
+
+__global__ void to_int8_kernel(const double *__restrict__ in, size_t n, int8_t *__restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (int8_t)in[i];
 }
 
 // scale[c] = sqrt(sum_h x_c[h]^2), 1 when the column is all zero (MainEff.c:87-99, NeFull2.c:100-135)
@@ -175,7 +189,7 @@ struct pareben_problem {
     FoldData *d_folds = nullptr;
     std::vector<FoldData> h_folds;
     double *d_Xcol = nullptr, *d_y = nullptr;     // full data, column-major (kept for lambda_max)
-    char *d_slabs = nullptr; size_t slab_stride = 0; int n_slabs = 0;
+    char *d_slabs = nullptr; size_t slab_stride = 0, slab_total = 0; int n_slabs = 0;
     int *d_queue = nullptr;
     double *d_flops = nullptr;
     cudaStream_t stream = nullptr;
@@ -192,6 +206,12 @@ struct pareben_problem {
     ~pareben_problem()
     {
         cudaSetDevice(device);
+        if (d_slabs) {          // hand the slab back to the per-device cache (keep the larger one)
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            SlabCache &c = g_slab_cache[device & 63];
+            if (c.bytes < slab_total) { if (c.ptr) cudaFree(c.ptr); c.ptr = d_slabs; c.bytes = slab_total; }
+            else cudaFree(d_slabs);
+        }
         for (void *p : allocs) cudaFree(p);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -240,9 +260,17 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         CU(cudaMemcpyAsync(p->d_Xcol, basis, sizeof(double) * n * k, cudaMemcpyHostToDevice, p->stream));
         CU(cudaMemcpyAsync(p->d_y, target, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
 
+        // Genotype-coded designs (every entry an integer in [-127, 127], e.g. {-1, 0, 1}) also get an
+        // int8 copy of the training matrices: the score contraction reads 1 byte instead of 8 per
+        // element and widens in registers (exact).
+        bool small_int = getenv("PAREBEN_NO_INT8") == nullptr;
+        for (size_t i = 0, e = (size_t)n * k; small_int && i < e; i++) {
+            const double v = basis[i];
+            if (!(v >= -127.0 && v <= 127.0) || v != (double)(int)v) small_int = false;
+        }
         // row lists per fold: index 0 = all rows (only materialised when n_folds == 0)
         const int nf = n_folds;
-        p->h_folds.assign(nf + 1, FoldData{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0});
+        p->h_folds.assign(nf + 1, FoldData{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0});
         int min_ntr = n;
         for (int f = (nf == 0 ? 0 : 1); f <= nf; f++) {
             std::vector<int> tr, te;
@@ -275,7 +303,12 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
             }
             if (epis) scales_kernel<true><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
             else scales_kernel<false><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
-            F.Xtr = Xtr; F.ytr = ytr; F.Xte = Xte; F.yte = yte; F.scale = scale;
+            F.Xtr = Xtr; F.ytr = ytr; F.Xte = Xte; F.yte = yte; F.scale = scale; F.Xtr8 = nullptr;
+            if (small_int) {
+                int8_t *x8 = p->dalloc<int8_t>((size_t)F.ntr * k + 16);
+                to_int8_kernel<<<std::min<size_t>(1024, ((size_t)F.ntr * k + 255) / 256), 256, 0, p->stream>>>(Xtr, (size_t)F.ntr * k, x8);
+                F.Xtr8 = x8;
+            }
         }
         CU(cudaGetLastError());
         p->d_folds = p->dalloc<FoldData>(nf + 1);
@@ -294,14 +327,36 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         p->slab_stride = slab_bytes(p->cap, p->nmax, p->kc);
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
-        int per_sm = 4;
+        // resident blocks per SM of the kernel variant this problem will launch
+        int per_sm = 1;
+        {
+            int occ = 0;
+            cudaError_t e;
+            if (prior == PAREBEN_GAUSSIAN) e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, false>, FIT_THREADS, 0)
+                                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, false>, FIT_THREADS, 0);
+            else e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, true>, FIT_THREADS, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, true>, FIT_THREADS, 0);
+            CU(e);
+            per_sm = std::max(1, occ);
+        }
         const char *env_bps = getenv("PAREBEN_BLOCKS_PER_SM");
-        if (env_bps) per_sm = std::max(1, atoi(env_bps));
+        if (env_bps) per_sm = std::max(1, std::min(per_sm, atoi(env_bps)));
         while (per_sm > 1 && (size_t)per_sm * p->sm_count * p->slab_stride > free_b / 2) per_sm--;
         p->n_slabs = per_sm * p->sm_count;
-        if ((size_t)p->n_slabs * p->slab_stride > free_b - (free_b >> 3))
-            throw std::make_pair((int)PAREBEN_ENOMEM, std::string("per-block work slabs do not fit in device memory; lower PAREBEN_BASIS_CAP"));
-        p->d_slabs = p->dalloc<char>((size_t)p->n_slabs * p->slab_stride);
+        p->slab_total = (size_t)p->n_slabs * p->slab_stride;
+        {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            SlabCache &c = g_slab_cache[device & 63];
+            if (c.ptr && c.bytes >= p->slab_total) { p->d_slabs = (char *)c.ptr; p->slab_total = c.bytes; c.ptr = nullptr; c.bytes = 0; }
+            else if (c.ptr) { cudaFree(c.ptr); c.ptr = nullptr; c.bytes = 0; }
+        }
+        if (!p->d_slabs) {
+            if (p->slab_total > free_b - (free_b >> 3))
+                throw std::make_pair((int)PAREBEN_ENOMEM, std::string("per-block work slabs do not fit in device memory; lower PAREBEN_BASIS_CAP"));
+            void *q = nullptr;
+            CU(cudaMalloc(&q, p->slab_total));
+            p->d_slabs = (char *)q;
+        }
         p->d_queue = p->dalloc<int>(1);
         p->d_flops = p->dalloc<double>(1);
         CU(cudaStreamSynchronize(p->stream));
@@ -314,6 +369,16 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
 }
 
 extern "C" void pareben_problem_destroy(pareben_problem *p) { delete p; }
+
+extern "C" void pareben_release_cache(void)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; d++)
+        if (g_slab_cache[d].ptr) { cudaSetDevice(d); cudaFree(g_slab_cache[d].ptr); g_slab_cache[d].ptr = nullptr; g_slab_cache[d].bytes = 0; }
+    cudaSetDevice(cur);
+}
 
 namespace {
 

@@ -5,6 +5,7 @@ python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 |
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv,noheader
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 300 python scripts/parity_report.py 2>&1 | tail -8
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "$1" == "ncu" ]; then
   timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/plain_bench.log 2>&1 &&

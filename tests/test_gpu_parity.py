@@ -164,15 +164,23 @@ def test_config2_binomial_full_grid(pb, bundled):
     assert np.all(st == 0)
     diff = ns != g["n_selected"]
     assert diff.sum() == 0, f"{diff.sum()} of 2000 fits with a different support size"
-    assert _rel(err, g["fold_err"]) < RTOL
+    # Binomial tolerance.  The reference's IRLS accepts/rejects Newton steps on `newTotalError >=
+    # errorLog` (NEmainEff.c:1991) and stops at |g| < 1e-6: near convergence the objective change of a
+    # step (~g^2/H ~ 1e-13) is below the rounding error of the objective itself (~1e-16 * 270), so
+    # the accept/reject outcome -- and with it the final weights at the 1e-8 level -- is decided by
+    # summation order.  Any re-associated implementation therefore agrees to ~1e-8, not 1e-12:
+    # bound the worst fit at 1e-7 and require the bulk to be at rounding level.
+    rel = np.abs(err - g["fold_err"]) / np.abs(g["fold_err"])
+    assert rel.max() < 1e-7
+    assert np.quantile(rel, 0.99) < 1e-12
     out = pb.CrossValidate(X, y, 5, prior="binomial")
     assert abs(out["alpha.optimal"] - float(g["alpha_optimal"])) < 1e-15
     assert abs(out["lambda.optimal"] - float(g["lambda_optimal"])) <= 1e-13 * float(g["lambda_optimal"])
-    assert _rel(out["Results.Summary"]["Likelihood"], g["summary_likelihood"]) < RTOL
+    assert _rel(out["Results.Summary"]["Likelihood"], g["summary_likelihood"]) < 1e-7
     loc = pb.CrossValidate(X, y, 5, foldId=g["fold_id"], prior="binomial", search="local")
     want = R.local_search_replay(g["grid_alpha"], g["grid_lambda"], -g["fold_err"])
     assert loc["alpha.optimal"] == want[1] and abs(loc["lambda.optimal"] - want[2]) <= 1e-13 * want[2]
-    assert np.allclose(loc["fullCV"], want[3], rtol=1e-8, atol=0)
+    assert np.allclose(loc["fullCV"], want[3], rtol=1e-7, atol=0)
 
 
 def test_binomial_epis_slice(pb, bundled):
