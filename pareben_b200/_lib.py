@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpareben.so")
+LIB_PATH = os.environ.get("PAREBEN_LIB") or os.path.join(_HERE, "libpareben.so")
 
 GAUSSIAN, BINOMIAL = 0, 1
 FIT_BASIS_CAP, FIT_NOT_PD, FIT_NONFINITE, FIT_ITER_MAX = 1, 2, 4, 8

@@ -145,7 +145,7 @@ __device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab
                                        const Scratch &sc)
 {   // fEBCatFullStat* (NEmainEff.c:1633-1803, NeFull.c:848-993)
     const int N = F.ntr, K = P.K, Kc = P.Kc, T = blockDim.x;
-    const double *X = F.Xtr, *t = F.ytr, *scale = F.scale;
+    const double *t = F.ytr, *scale = F.scale;
     post_mode<EPIS>(s, b, N, t, sc);
     const int M = b.M;
     double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2;
@@ -168,7 +168,7 @@ __device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab
             if (r == 0) s.S_in[c] = acc;
             else if (r == 1) s.Q_in[c] = acc;
             else s.G[(size_t)s.grow[r - 2] * Kc + c] = acc / scale[c];
-        }, sV, true);
+        }, s.vbuf, (int)vld(P.cap), sV, true);
     quad_forms(s, s.sigma, s.sigma_new, M, Kc, nullptr, [&](int c, double quad, double) {
         const double sc_c = scale[c];
         s.S_in[c] = s.S_in[c] / (sc_c * sc_c) - quad;
@@ -324,7 +324,7 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                             if (need_sq) {
                                 contract_x<EPIS>(F, K, Kc, 1,
                                     [&](int, int h) { return s.phinew[h] * s.w1[h]; },
-                                    [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, sV);
+                                    [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, s.vbuf, (int)vld(cap), sV);
                             }
                             {   // tmp = PHI' (w o phi_new), one warp per active column
                                 const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;

@@ -61,6 +61,7 @@ struct FitOutputs {
 struct Slab {
     double *sigma, *sigma_new, *H;      // cap*cap each
     double *phi;                        // nmax * cap, column-major (column j at phi + j*N)
+    double *vbuf;                       // (nmax + 64) * vld(cap): right-hand sides of a contraction, row-major
     double *G;                          // cap * Kc: physical rows, row r at G + r*Kc
     double *xt, *S_in, *Q_in, *S_out, *Q_out, *dml, *aroot;   // Kc each
     double *t, *e, *phinew, *w1, *w2;   // nmax each
@@ -74,9 +75,11 @@ struct Slab {
 // 32-byte loads.
 __host__ __device__ inline size_t sig_elems(int cap) { return (((size_t)cap * (cap + 8)) + 3) & ~(size_t)3; }
 
+__host__ __device__ inline size_t vld(int cap) { return ((size_t)cap + 2 + 15) & ~(size_t)15; }   // leading dimension of vbuf
+
 __host__ __device__ inline size_t slab_doubles(int cap, int nmax, int Kc)
 {
-    return 3 * sig_elems(cap) + (size_t)nmax * cap + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
+    return 3 * sig_elems(cap) + (size_t)nmax * cap + (size_t)(nmax + 64) * vld(cap) + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
            (size_t)6 * (cap + 1);
 }
 __host__ __device__ inline size_t slab_ints(int cap, int Kc) { return (size_t)2 * cap + (size_t)5 * Kc; }
@@ -93,6 +96,7 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
     s.sigma = d; d += sig_elems(cap);
     s.sigma_new = d; d += sig_elems(cap);
     s.H = d; d += sig_elems(cap);
+    s.vbuf = d; d += (size_t)(nmax + 64) * vld(cap);      // right after the 32-byte aligned matrices -> 32-byte aligned
     s.phi = d; d += (size_t)nmax * cap;
     s.G = d; d += (size_t)cap * Kc;
     s.xt = d; d += Kc; s.S_in = d; d += Kc; s.Q_in = d; d += Kc; s.S_out = d; d += Kc; s.Q_out = d; d += Kc;
@@ -215,10 +219,16 @@ struct Cand {
         if (EPIS) return i == j ? Xrow[i] : Xrow[i] * Xrow[j];
         return Xrow[i];
     }
+    // int -> double without the (quarter-rate) I2F conversion: 2^52 + 2^31 + v is representable and its
+    // low word is 0x80000000 ^ v, so one XOR and one FP64 subtract give v exactly.
+    static __device__ inline double small_int_to_double(int v)
+    {
+        return __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)v)) - 4503601774854144.0;
+    }
     __device__ inline double at(const int8_t *Xrow) const      // exact: |x| <= 127, products <= 2^14
     {
-        if (EPIS) return i == j ? (double)Xrow[i] : (double)((int)Xrow[i] * (int)Xrow[j]);
-        return (double)Xrow[i];
+        if (EPIS) return small_int_to_double(i == j ? (int)Xrow[i] : (int)Xrow[i] * (int)Xrow[j]);
+        return small_int_to_double((int)Xrow[i]);
     }
 };
 

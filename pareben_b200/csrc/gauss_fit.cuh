@@ -12,6 +12,7 @@
 // pair columns for Epis are generated on the fly from two loci and never stored.
 #pragma once
 #include "common.cuh"
+#include <cuda_pipeline.h>
 
 namespace pareben {
 
@@ -23,83 +24,110 @@ struct GaussState {
 };
 
 // ---- contraction: out(r, c) = sum_h x_c[h] * V_r[h]  for r in [0,R), c in [0,Kc) -------------
-// Thread-per-candidate, RC right-hand sides per pass kept in registers; the V tile is staged in
-// shared memory ([TH rows][RC]) so every X element fetched from L2/L1 feeds RC FMAs.  X loads run
-// PF rows ahead of the FMAs (software prefetch) because with ~16 warps per SM it is load latency,
-// not the FP64 pipe, that limits this loop.
+// The right-hand sides are first written to a row-major buffer V[h][r] in global memory (leading
+// dimension ldv; rows zero-padded to a multiple of TH, columns to a multiple of RC).  Tiles of
+// TH rows x RC columns are then streamed into shared memory with cp.async, double-buffered, so the
+// copy of tile s+1 overlaps the FMAs of tile s and there is ONE barrier per tile.  Every thread
+// owns one candidate and keeps RC accumulators in registers: per row it needs one element of the
+// shared training matrix (int8 or f64, prefetched PF rows ahead) and RC values of V, broadcast
+// from shared memory with 32-byte loads.
 // Summation over rows is sequential in h for every (r, c): identical arithmetic for identical
 // columns, so exact duplicates tie exactly.
 //   colval(r, h)  value of right-hand side r at row h (the caller folds any row weight in)
 //   sq_first      when true, right-hand side 0 is contracted with x^2 instead of x
 //                 (the binomial sum_h w[h] x^2, NEmainEff.c:1728-1729)
-constexpr int RC = 8;     // right-hand sides per register tile
-constexpr int TH = 128;   // rows per shared-memory tile
-constexpr int PF = 8;     // rows of X prefetched per group
+#ifndef PAREBEN_RC
+#define PAREBEN_RC 16
+#endif
+constexpr int RC = PAREBEN_RC;    // right-hand sides per register tile
+constexpr int TH = 64;            // rows per shared-memory tile
+constexpr int PF = 8;             // rows of X prefetched per group
+constexpr int SV_DOUBLES = 2 * TH * RC;
+
+__device__ inline void stage_tile(double *dst, const double *__restrict__ V, int ldv, int h0, int r0)
+{   // TH rows x RC doubles, 16 bytes per cp.async
+    constexpr int CH = RC / 2;                 // 16-byte chunks per row
+    for (int idx = threadIdx.x; idx < TH * CH; idx += blockDim.x) {
+        const int h = idx / CH, q = idx - h * CH;
+        __pipeline_memcpy_async(dst + h * RC + 2 * q, V + (size_t)(h0 + h) * ldv + r0 + 2 * q, 16);
+    }
+    __pipeline_commit();
+}
 
 template <bool EPIS, class XT, class ColVal, class Store>
 __device__ inline void contract(const XT *__restrict__ X, int N, int K, int Kc, int R, ColVal colval,
-                                Store store, double *sV /* TH*RC doubles */, bool sq_first = false)
+                                Store store, double *__restrict__ V, int ldv, double *sV, bool sq_first = false)
 {
     const int T = blockDim.x;
+    const int nchunk = (R + RC - 1) / RC, ntile = (N + TH - 1) / TH;
+    const int Rp = nchunk * RC, Np = ntile * TH;
+    __syncthreads();
+    for (int r = 0; r < Rp; r++)                                  // h fastest: coalesced reads of the column-major sources
+        for (int h = threadIdx.x; h < Np; h += T) V[(size_t)h * ldv + r] = (r < R && h < N) ? colval(r, h) : 0.0;
+    __syncthreads();
+    const int nstep = nchunk * ntile;
     for (int c0 = 0; c0 < Kc; c0 += T) {
         const int c = c0 + threadIdx.x;
         const bool live = c < Kc;
         Cand<EPIS> cd(live ? c : 0, K);
-        for (int r0 = 0; r0 < R; r0 += RC) {
-            const int nr = min(RC, R - r0);
-            const bool sq = sq_first && r0 == 0;
-            double acc[RC];
+        double acc[RC];
 #pragma unroll
-            for (int r = 0; r < RC; r++) acc[r] = 0.0;
-            for (int h0 = 0; h0 < N; h0 += TH) {
-                const int nh = min(TH, N - h0);
-                const int nh8 = (nh + PF - 1) / PF * PF;          // rows past nh are staged as zeros
-                __syncthreads();
-                for (int idx = threadIdx.x; idx < nh8 * RC; idx += T) {
-                    const int r = idx / nh8, h = idx - r * nh8;    // consecutive threads -> consecutive rows (coalesced)
-                    sV[h * RC + r] = (r < nr && h < nh) ? colval(r0 + r, h0 + h) : 0.0;
-                }
-                __syncthreads();
-                if (live) {
-                    double xv[PF];
-#pragma unroll
-                    for (int i = 0; i < PF; i++) xv[i] = cd.at(X + (size_t)min(h0 + i, N - 1) * K);
-                    for (int hh = 0; hh < nh8; hh += PF) {
-                        double xn[PF];
-                        const int hb = h0 + hh + PF;
-#pragma unroll
-                        for (int i = 0; i < PF; i++) xn[i] = cd.at(X + (size_t)min(hb + i, N - 1) * K);   // next group in flight
-#pragma unroll
-                        for (int i = 0; i < PF; i++) {
-                            const double x = xv[i];
-                            const double4 *v4 = reinterpret_cast<const double4 *>(sV + (hh + i) * RC);
-                            const double4 a = v4[0], b = v4[1];
-                            acc[0] = fma(sq ? x * x : x, a.x, acc[0]); acc[1] = fma(x, a.y, acc[1]);
-                            acc[2] = fma(x, a.z, acc[2]); acc[3] = fma(x, a.w, acc[3]);
-                            acc[4] = fma(x, b.x, acc[4]); acc[5] = fma(x, b.y, acc[5]);
-                            acc[6] = fma(x, b.z, acc[6]); acc[7] = fma(x, b.w, acc[7]);
-                        }
-#pragma unroll
-                        for (int i = 0; i < PF; i++) xv[i] = xn[i];
-                    }
-                }
+        for (int r = 0; r < RC; r++) acc[r] = 0.0;
+        stage_tile(sV, V, ldv, 0, 0);
+        __pipeline_wait_prior(0);
+        __syncthreads();
+        for (int st = 0; st < nstep; st++) {
+            const int chunk = st / ntile, tile = st - chunk * ntile;
+            const int r0 = chunk * RC, h0 = tile * TH;
+            const double *buf = sV + (st & 1) * (TH * RC);
+            if (st + 1 < nstep) {                                   // next tile in flight while this one is consumed
+                const int c2 = (st + 1) / ntile, t2 = (st + 1) - c2 * ntile;
+                stage_tile(sV + ((st + 1) & 1) * (TH * RC), V, ldv, t2 * TH, c2 * RC);
             }
             if (live) {
+                const bool sq = sq_first && r0 == 0;
+                const int nh = min(TH, N - h0);
+                double xv[PF];
 #pragma unroll
-                for (int r = 0; r < RC; r++) if (r < nr) store(r0 + r, c, acc[r]);
+                for (int i = 0; i < PF; i++) xv[i] = cd.at(X + (size_t)min(h0 + i, N - 1) * K);
+                for (int hh = 0; hh < nh; hh += PF) {
+                    double xn[PF];
+#pragma unroll
+                    for (int i = 0; i < PF; i++) xn[i] = cd.at(X + (size_t)min(h0 + hh + PF + i, N - 1) * K);
+#pragma unroll
+                    for (int i = 0; i < PF; i++) {
+                        const double x = xv[i];
+                        const double4 *v4 = reinterpret_cast<const double4 *>(buf + (hh + i) * RC);
+#pragma unroll
+                        for (int q = 0; q < RC / 4; q++) {
+                            const double4 a = v4[q];
+                            acc[4 * q + 0] = fma((q == 0 && sq) ? x * x : x, a.x, acc[4 * q + 0]);
+                            acc[4 * q + 1] = fma(x, a.y, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fma(x, a.z, acc[4 * q + 2]);
+                            acc[4 * q + 3] = fma(x, a.w, acc[4 * q + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < PF; i++) xv[i] = xn[i];
+                }
+                if (tile == ntile - 1) {
+#pragma unroll
+                    for (int r = 0; r < RC; r++) { if (r0 + r < R) store(r0 + r, c, acc[r]); acc[r] = 0.0; }
+                }
             }
+            __pipeline_wait_prior(0);
+            __syncthreads();
         }
     }
-    __syncthreads();
 }
 
 // Dispatch on the storage type of the shared training matrix (int8 genotype codes when available).
 template <bool EPIS, class ColVal, class Store>
-__device__ inline void contract_x(const FoldData &F, int K, int Kc, int R, ColVal colval, Store store, double *sV,
-                                  bool sq_first = false)
+__device__ inline void contract_x(const FoldData &F, int K, int Kc, int R, ColVal colval, Store store, double *V, int ldv,
+                                  double *sV, bool sq_first = false)
 {
-    if (F.Xtr8) contract<EPIS, int8_t>(F.Xtr8, F.ntr, K, Kc, R, colval, store, sV, sq_first);
-    else contract<EPIS, double>(F.Xtr, F.ntr, K, Kc, R, colval, store, sV, sq_first);
+    if (F.Xtr8) contract<EPIS, int8_t>(F.Xtr8, F.ntr, K, Kc, R, colval, store, V, ldv, sV, sq_first);
+    else contract<EPIS, double>(F.Xtr, F.ntr, K, Kc, R, colval, store, V, ldv, sV, sq_first);
 }
 
 // Quadratic forms of the candidate cache against the active-set inverse:
@@ -420,7 +448,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                 [&](int r, int c, double acc) {
                     if (r < M) s.G[(size_t)s.grow[r] * Kc + c] = acc / scale[c];
                     else s.xt[c] = acc / scale[c];
-                }, sV);
+                }, s.vbuf, (int)vld(cap), sV);
             if (threadIdx.x == 0) g.flops += 2.0 * N * (double)Kc * (M + 1);
         }
         int i_iter = 0;
@@ -507,7 +535,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             const int grow_new = s.grow[M];
                             contract_x<EPIS>(F, K, Kc, 1,
                                 [&](int, int h) { return s.phinew[h]; },
-                                [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, sV);
+                                [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, s.vbuf, (int)vld(cap), sV);
                             phi_dot(s.phi, N, M, s.phinew, s.tmp, g.beta);             // tmp = beta PHI' phi
                             for (int i = threadIdx.x; i < M; i += T) {
                                 double z = 0;

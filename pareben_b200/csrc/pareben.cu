@@ -9,6 +9,7 @@
 #include "binom_fit.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <cstdio>
 #include <cstdlib>
@@ -24,12 +25,43 @@ thread_local std::string g_err;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
-// Per-device cache of the big per-block work slab: a CrossValidate call would otherwise pay a
-// multi-GB cudaMalloc/cudaFree every time.  One buffer per device is kept between calls and
-// released by pareben_release_cache() (or at process exit).
-struct SlabCache { void *ptr = nullptr; size_t bytes = 0; };
-SlabCache g_slab_cache[64];
+// Per-device pool of device allocations.  cudaMalloc/cudaFree synchronise the device and can
+// take hundreds of milliseconds for multi-GB buffers, which would dominate a CrossValidate call
+// on a small problem; freed buffers are therefore parked here (exact-size reuse, or best fit for
+// the big work slab) and only returned to the driver by pareben_release_cache().
+struct PoolEntry { void *ptr; size_t bytes; };
+struct DevPool { std::vector<PoolEntry> free_list; size_t parked = 0; };
+DevPool g_pool[64];
 std::mutex g_cache_mu;
+constexpr size_t POOL_MAX_ENTRIES = 512;
+
+void *pool_take(int device, size_t bytes, bool best_fit, size_t *got)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    DevPool &pl = g_pool[device & 63];
+    int pick = -1;
+    for (int i = 0; i < (int)pl.free_list.size(); i++) {
+        const size_t b = pl.free_list[i].bytes;
+        if (b == bytes) { pick = i; break; }
+        if (best_fit && b > bytes && b <= bytes + bytes / 2 && (pick < 0 || b < pl.free_list[pick].bytes)) pick = i;
+    }
+    if (pick < 0) return nullptr;
+    PoolEntry e = pl.free_list[pick];
+    pl.free_list.erase(pl.free_list.begin() + pick);
+    pl.parked -= e.bytes;
+    if (got) *got = e.bytes;
+    return e.ptr;
+}
+
+void pool_give(int device, void *ptr, size_t bytes)
+{
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    DevPool &pl = g_pool[device & 63];
+    if (pl.free_list.size() >= POOL_MAX_ENTRIES) { cudaFree(ptr); return; }
+    pl.free_list.push_back(PoolEntry{ptr, bytes});
+    pl.parked += bytes;
+}
 
 #define CU(call)                                                                                  \
     do {                                                                                          \
@@ -115,11 +147,11 @@ __global__ void lambda_max_kernel(const double *__restrict__ X, int N, int K, in
 constexpr int FIT_THREADS = 256;
 
 template <bool EPIS, bool BINOMIAL>
-__global__ void __launch_bounds__(FIT_THREADS)
+__global__ void __launch_bounds__(FIT_THREADS, 2)
 eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_tasks, int *queue, char *slabs,
                 size_t slab_stride, FitOutputs out)
 {
-    __shared__ __align__(32) double sV[TH * RC];
+    __shared__ __align__(32) double sV[SV_DOUBLES];      // double-buffered right-hand-side tiles of the contraction
     __shared__ double red[66];
     __shared__ int redi[66];
     __shared__ int s_task;
@@ -185,7 +217,7 @@ struct pareben_problem {
     int device = 0;
     int n = 0, k = 0, kc = 0, n_folds = 0, epis = 0, prior = 0, cap = 0, nmax = 0;
     int sm_count = 0;
-    std::vector<void *> allocs;          // everything cudaMalloc'ed for this problem
+    std::vector<PoolEntry> allocs;       // every device buffer of this problem (returned to the pool on destroy)
     FoldData *d_folds = nullptr;
     std::vector<FoldData> h_folds;
     double *d_Xcol = nullptr, *d_y = nullptr;     // full data, column-major (kept for lambda_max)
@@ -198,21 +230,17 @@ struct pareben_problem {
 
     template <class T> T *dalloc(size_t n)
     {
-        void *p = nullptr;
-        CU(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-        allocs.push_back(p);
+        const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
+        void *p = pool_take(device, bytes, false, nullptr);
+        if (!p) CU(cudaMalloc(&p, bytes));
+        allocs.push_back(PoolEntry{p, bytes});
         return static_cast<T *>(p);
     }
     ~pareben_problem()
     {
         cudaSetDevice(device);
-        if (d_slabs) {          // hand the slab back to the per-device cache (keep the larger one)
-            std::lock_guard<std::mutex> lk(g_cache_mu);
-            SlabCache &c = g_slab_cache[device & 63];
-            if (c.bytes < slab_total) { if (c.ptr) cudaFree(c.ptr); c.ptr = d_slabs; c.bytes = slab_total; }
-            else cudaFree(d_slabs);
-        }
-        for (void *p : allocs) cudaFree(p);
+        pool_give(device, d_slabs, slab_total);
+        for (const PoolEntry &e : allocs) pool_give(device, e.ptr, e.bytes);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -345,10 +373,9 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         p->n_slabs = per_sm * p->sm_count;
         p->slab_total = (size_t)p->n_slabs * p->slab_stride;
         {
-            std::lock_guard<std::mutex> lk(g_cache_mu);
-            SlabCache &c = g_slab_cache[device & 63];
-            if (c.ptr && c.bytes >= p->slab_total) { p->d_slabs = (char *)c.ptr; p->slab_total = c.bytes; c.ptr = nullptr; c.bytes = 0; }
-            else if (c.ptr) { cudaFree(c.ptr); c.ptr = nullptr; c.bytes = 0; }
+            size_t got = 0;
+            void *q = pool_take(device, p->slab_total, true, &got);
+            if (q) { p->d_slabs = (char *)q; p->slab_total = got; }
         }
         if (!p->d_slabs) {
             if (p->slab_total > free_b - (free_b >> 3))
@@ -375,8 +402,12 @@ extern "C" void pareben_release_cache(void)
     std::lock_guard<std::mutex> lk(g_cache_mu);
     int cur = 0;
     cudaGetDevice(&cur);
-    for (int d = 0; d < 64; d++)
-        if (g_slab_cache[d].ptr) { cudaSetDevice(d); cudaFree(g_slab_cache[d].ptr); g_slab_cache[d].ptr = nullptr; g_slab_cache[d].bytes = 0; }
+    for (int d = 0; d < 64; d++) {
+        if (g_pool[d].free_list.empty()) continue;
+        cudaSetDevice(d);
+        for (const PoolEntry &e : g_pool[d].free_list) cudaFree(e.ptr);
+        g_pool[d].free_list.clear(); g_pool[d].parked = 0;
+    }
     cudaSetDevice(cur);
 }
 
@@ -390,6 +421,7 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
     if (!p || n_fits < 0 || (n_fits > 0 && (!fold || !alpha || !lambda))) return fail(PAREBEN_EINVAL, "pareben_run_fits: bad argument");
     if (n_fits == 0) return PAREBEN_OK;
     void *scratch[8] = {nullptr};
+    size_t scratch_bytes[8] = {0};
     int ns = 0;
     try {
         CU(cudaSetDevice(p->device));
@@ -401,7 +433,11 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
         }
         // expected cost grows as lambda falls (larger active sets): longest fits first
         std::stable_sort(tasks.begin(), tasks.end(), [](const FitTask &a, const FitTask &b) { return a.lambda < b.lambda; });
-        auto tmp_alloc = [&](size_t bytes) { void *q = nullptr; CU(cudaMalloc(&q, std::max<size_t>(bytes, 8))); scratch[ns++] = q; return q; };
+        auto tmp_alloc = [&](size_t bytes) {
+            bytes = (std::max<size_t>(bytes, 8) + 255) & ~(size_t)255;
+            void *q = pool_take(p->device, bytes, false, nullptr);
+            if (!q) CU(cudaMalloc(&q, bytes));
+            scratch_bytes[ns] = bytes; scratch[ns++] = q; return q; };
         FitTask *d_tasks = (FitTask *)tmp_alloc(sizeof(FitTask) * n_fits);
         double *d_err = (double *)tmp_alloc(sizeof(double) * n_fits);
         int *d_ints = (int *)tmp_alloc(sizeof(int) * 3 * n_fits);
@@ -457,9 +493,9 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
             CU(cudaMemcpy(hb, dump->beta, sizeof(double) * (2 * p->cap + 4), cudaMemcpyDeviceToHost));
             dump->m = hm; dump->used = hm + 1; dump->beta = hb; dump->var = hb + p->cap; dump->scalars = hb + 2 * p->cap;
         }
-        for (int i = 0; i < ns; i++) cudaFree(scratch[i]);
+        for (int i = 0; i < ns; i++) pool_give(p->device, scratch[i], scratch_bytes[i]);
     } catch (std::pair<int, std::string> &e) {
-        for (int i = 0; i < ns; i++) cudaFree(scratch[i]);
+        for (int i = 0; i < ns; i++) pool_give(p->device, scratch[i], scratch_bytes[i]);
         return fail(e.first, e.second);
     }
     return PAREBEN_OK;
@@ -508,8 +544,11 @@ extern "C" int pareben_cv_grid(const double *basis, int n, int k, const double *
     const int m = (int)mine.size();
     if (m == 0) return PAREBEN_OK;
     pareben_problem *p = nullptr;
+    const bool timing = getenv("PAREBEN_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     int rc = pareben_problem_create(&p, device, basis, n, k, target, fold_id, n_folds, epis, prior);
     if (rc != PAREBEN_OK) return rc;
+    auto t1 = std::chrono::steady_clock::now();
     std::vector<int> fold(m), st(m), ns(m);
     std::vector<double> a(m), l(m), err(m);
     for (int i = 0; i < m; i++) {
@@ -517,7 +556,15 @@ extern "C" int pareben_cv_grid(const double *basis, int n, int k, const double *
         fold[i] = fit % n_folds + 1; a[i] = alpha[fit / n_folds]; l[i] = lambda[fit / n_folds];
     }
     rc = pareben_run_fits(p, m, fold.data(), a.data(), l.data(), err.data(), st.data(), ns.data(), nullptr);
+    auto t2 = std::chrono::steady_clock::now();
+    const double kernel_ms = p->last_ms;
     pareben_problem_destroy(p);
+    if (timing) {
+        auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[pareben] cv_grid: create %.2f ms, run_fits %.2f ms (kernel %.2f ms), destroy %.2f ms\n",
+                ms(t0, t1), ms(t1, t2), kernel_ms, ms(t2, t3));
+    }
     if (rc != PAREBEN_OK) return rc;
     for (int i = 0; i < m; i++) {
         fold_err[mine[i]] = err[i];
