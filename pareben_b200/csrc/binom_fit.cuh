@@ -71,46 +71,26 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
             w[h] = bw; h0 += bw;
         }
         block_sum2(g0, h0, sc);
-        if (threadIdx.x == 0) { g[0] = g0; s.H[0] = h0; }
+        if (threadIdx.x == 0) g[0] = g0;
+        (void)h0;
         __syncthreads();
-        // gradient, first row/column, and the upper triangle of PHI' B PHI (+ diag(alpha)).
-        // One warp per (j, block of 8 columns k >= j): lanes stride the rows, phi_j[h] w[h] is
-        // formed once and reused for the 8 products, as the reference's (phi_j * beta) * phi_k order.
-        const int m1 = M - 1;
+        // gradient g_j = phi_j'e - alpha_j mu_j (one warp per column), then the Hessian PHI'B PHI + diag(0, alpha)
+        // as a tiled Gram matrix; column 0 of PHI is the intercept's all-ones column, so H(0, k) = sum w phi_k
+        // and H(0, 0) = sum w come out of the same pass (:1887-1919).
         for (int j = 1 + wid; j < M; j += nw) {
             const double *ph = s.phi + (size_t)j * N;
-            double gj = 0, hj = 0;
-            for (int h = lane; h < N; h += 32) { gj = fma(ph[h], e[h], gj); hj = fma(w[h], ph[h], hj); }
-            gj = warp_sum(gj); hj = warp_sum(hj);
-            if (lane == 0) { g[j] = gj - s.alpha[j - 1] * s.mu[j]; s.H[j] = hj; s.H[j * M] = hj; }
+            double gj = 0;
+            for (int h = lane; h < N; h += 32) gj = fma(ph[h], e[h], gj);
+            gj = warp_sum(gj);
+            if (lane == 0) g[j] = gj - s.alpha[j - 1] * s.mu[j];
         }
-        const int kb = (m1 + 7) / 8;                 // column blocks
-        for (int item = wid; item < m1 * kb; item += nw) {
-            const int j = item / kb + 1, k0 = (item - (j - 1) * kb) * 8 + 1;
-            if (k0 + 7 < j) continue;                // block entirely below the diagonal
-            const double *a = s.phi + (size_t)j * N;
-            double z[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) z[q] = 0.0;
-            for (int h = lane; h < N; h += 32) {
-                const double aw = a[h] * w[h];
-#pragma unroll
-                for (int q = 0; q < 8; q++) { const int k = min(k0 + q, m1); z[q] = fma(aw, s.phi[(size_t)k * N + h], z[q]); }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const double zz = warp_sum(z[q]);
-                const int k = k0 + q;
-                if (lane == 0 && k <= m1 && k >= j) {
-                    const double val = (j == k) ? zz + s.alpha[k - 1] : zz;
-                    s.H[k * M + j] = val; s.H[j * M + k] = val;
-                }
-            }
-        }
-        __syncthreads();
+        gram_tiled(s.phi, N, M, w, sc.sweep, [&](int j, int k, double z) {
+            if (j == k && j > 0) z += s.alpha[k - 1];
+            s.H[k * M + j] = z; s.H[j * M + k] = z;
+        });
         for (int idx = threadIdx.x; idx < M * M; idx += T) s.sigma[idx] = s.H[idx];
         __syncthreads();
-        if (!spd_inverse_sweep(s.sigma, M, s.colk, sc)) b.status |= ST_NOT_PD;
+        if (!spd_inverse_sweep(s.sigma, M, s.colk, sc, sc.sweep)) b.status |= ST_NOT_PD;
         int cnt = 0;
         for (int j = EPIS ? 0 : 1; j < M; j++) cnt += fabs(g[j]) < 1e-6;
         for (int k = threadIdx.x; k < M; k += T) {

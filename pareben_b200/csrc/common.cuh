@@ -80,7 +80,7 @@ __host__ __device__ inline size_t vld(int cap) { return ((size_t)cap + 2 + 15) &
 __host__ __device__ inline size_t slab_doubles(int cap, int nmax, int Kc)
 {
     return 3 * sig_elems(cap) + (size_t)nmax * cap + (size_t)(nmax + 64) * vld(cap) + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
-           (size_t)6 * (cap + 1);
+           (size_t)7 * (cap + 1);
 }
 __host__ __device__ inline size_t slab_ints(int cap, int Kc) { return (size_t)2 * cap + (size_t)5 * Kc; }
 __host__ __device__ inline size_t slab_bytes(int cap, int nmax, int Kc)
@@ -103,7 +103,7 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
     s.dml = d; d += Kc; s.aroot = d; d += Kc;
     s.t = d; d += nmax; s.e = d; d += nmax; s.phinew = d; d += nmax; s.w1 = d; d += nmax; s.w2 = d; d += nmax;
     s.mu = d; d += cap + 1; s.alpha = d; d += cap + 1; s.gamma = d; d += cap + 1;
-    s.tmp = d; d += cap + 1; s.u = d; d += cap + 1; s.colk = d; d += cap + 1;
+    s.tmp = d; d += cap + 1; s.u = d; d += cap + 1; s.colk = d; d += 2 * (cap + 1);
     int *i = reinterpret_cast<int *>(d);
     s.used = i; i += cap; s.grow = i; i += cap;
     s.unused = i; i += Kc; s.upos = i; i += Kc; s.amap = i; i += Kc; s.action = i; i += Kc; s.block = i; i += Kc;
@@ -112,7 +112,7 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
 
 // ------------------------------------------------------------------------------------------
 // block-level primitives.  `red` is a shared scratch of >= 33 doubles, `redi` >= 33 ints.
-struct Scratch { double *red; int *redi; };
+struct Scratch { double *red; int *redi; double *sweep; /* SWEEP_SMEM_M^2 + 2*SWEEP_SMEM_M doubles, or null */ };
 
 __device__ inline double warp_sum(double v)
 {

@@ -190,32 +190,125 @@ __device__ inline void phi_dot(const double *phi, int N, int M, const double *v,
 // In-place inverse of a symmetric positive-definite M x M matrix (leading dimension M) by the
 // symmetric sweep operator.  Plays the role of dpotrf + dpotri (MainEff.c:1346-1369).  Returns
 // false (to every thread) when a pivot is not positive.
-__device__ inline bool spd_inverse_sweep(double *a, int M, double *colk, const Scratch &sc)
+//   * one barrier per pivot: the thread that rewrites entry (i, k+1) also publishes it as the next
+//     pivot column (double-buffered in `colbuf`, 2*M doubles);
+//   * warps own columns, lanes own rows (no integer division, conflict-free);
+//   * when M <= SWEEP_SMEM_M the matrix is swept inside shared memory (`sm`) and copied back.
+constexpr int SWEEP_SMEM_M = 64;
+
+__device__ inline bool sweep_core(double *a, int M, double *colbuf)
 {
-    const int T = blockDim.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double *cur = colbuf, *nxt = colbuf + M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) cur[i] = a[i];          // column 0
+    __syncthreads();
     bool ok = true;
     for (int k = 0; k < M; k++) {
-        const double d = a[k * M + k];
+        const double d = cur[k];
         if (!(d > 0.0)) { ok = false; break; }        // uniform: every thread reads the same value
-        for (int i = threadIdx.x; i < M; i += T) colk[i] = a[k * M + i];
-        __syncthreads();
         const double dinv = 1.0 / d;
-        for (int idx = threadIdx.x; idx < M * M; idx += T) {
-            const int j = idx / M, i = idx - j * M;
-            double v;
-            if (i == k && j == k) v = -dinv;
-            else if (i == k) v = colk[j] * dinv;
-            else if (j == k) v = colk[i] * dinv;
-            else v = a[idx] - (colk[i] * colk[j]) * dinv;
-            a[idx] = v;
+        for (int j = wid; j < M; j += nw) {
+            const double cj = cur[j];
+            double *col = a + (size_t)j * M;
+            for (int i = lane; i < M; i += 32) {
+                double v;
+                if (i == k && j == k) v = -dinv;
+                else if (i == k) v = cj * dinv;
+                else if (j == k) v = cur[i] * dinv;
+                else v = col[i] - (cur[i] * cj) * dinv;
+                col[i] = v;
+                if (j == k + 1) nxt[i] = v;
+            }
         }
         __syncthreads();
+        double *t = cur; cur = nxt; nxt = t;
     }
-    if (ok) {
-        for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -a[idx];
+    return ok;
+}
+
+__device__ inline bool spd_inverse_sweep(double *a, int M, double *colk, const Scratch &sc, double *sm = nullptr)
+{
+    const int T = blockDim.x;
+    bool ok;
+    if (sm && M <= SWEEP_SMEM_M) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < M * M; idx += T) sm[idx] = a[idx];
+        __syncthreads();
+        ok = sweep_core(sm, M, sm + SWEEP_SMEM_M * SWEEP_SMEM_M);
+        if (ok) for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -sm[idx];
+    } else {
+        ok = sweep_core(a, M, colk);          // colk: 2*(cap+1) doubles in the slab
+        if (ok) for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -a[idx];
     }
     __syncthreads();
     return ok;
+}
+
+// Gram matrix of the active columns, H(j, k) = sum_h (phi_j[h] * w[h]) * phi_k[h]  for j <= k (mirrored),
+// w = nullptr meaning all ones.  This is FinalUpdate*'s PHI'PHI (MainEff.c:1869-1874) and the IRLS
+// Hessian PHI'B PHI (NEmainEff.c:1911-1919, same (phi_j * beta) * phi_k order for the upper triangle
+// the Cholesky reads).  64 x 64 panels; per panel the block streams 32-row tiles of the two column
+// groups through shared memory and every thread accumulates a 4 x 4 register block over all rows
+// in ascending h -- 16 FMAs per four 16-byte shared loads, no shuffles.
+//   smem: 2 * GR_ROWS * GR_LD doubles.   out(j, k, value) is called once per j <= k.
+constexpr int GR_ROWS = 32, GR_COLS = 64, GR_LD = GR_COLS + 2;
+constexpr int GRAM_DOUBLES = 2 * GR_ROWS * GR_LD;
+
+template <class Out>
+__device__ inline void gram_tiled(const double *__restrict__ phi, int N, int M, const double *__restrict__ w,
+                                  double *sm, Out out)
+{
+    double *sA = sm, *sB = sm + GR_ROWS * GR_LD;
+    const int T = blockDim.x;
+    const int bj = threadIdx.x >> 4, bk = threadIdx.x & 15;      // 16 x 16 register blocks of 4 x 4 (first 256 threads)
+    const int npan = (M + GR_COLS - 1) / GR_COLS;
+    for (int pj = 0; pj < npan; pj++)
+        for (int pk = pj; pk < npan; pk++) {
+            const int j0 = pj * GR_COLS, k0 = pk * GR_COLS;
+            const bool active = threadIdx.x < 256 && (pj != pk || bj <= bk) && j0 + 4 * bj < M && k0 + 4 * bk < M;
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+            for (int h0 = 0; h0 < N; h0 += GR_ROWS) {
+                __syncthreads();
+                for (int idx = threadIdx.x; idx < GR_ROWS * GR_COLS; idx += T) {
+                    const int hl = idx & (GR_ROWS - 1), cl = idx >> 5;         // consecutive threads -> consecutive rows
+                    const int h = h0 + hl;
+                    double va = 0.0, vb = 0.0;
+                    if (h < N) {
+                        if (j0 + cl < M) { va = phi[(size_t)(j0 + cl) * N + h]; if (w) va *= w[h]; }
+                        if (k0 + cl < M) vb = phi[(size_t)(k0 + cl) * N + h];
+                    }
+                    sA[hl * GR_LD + cl] = va; sB[hl * GR_LD + cl] = vb;
+                }
+                __syncthreads();
+                if (active) {
+#pragma unroll 4
+                    for (int hl = 0; hl < GR_ROWS; hl++) {
+                        const double2 *pa = reinterpret_cast<const double2 *>(sA + hl * GR_LD + 4 * bj);
+                        const double2 *pb = reinterpret_cast<const double2 *>(sB + hl * GR_LD + 4 * bk);
+                        const double2 a01 = pa[0], a23 = pa[1], b01 = pb[0], b23 = pb[1];
+                        const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+                    }
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int j = j0 + 4 * bj + a, k = k0 + 4 * bk + b;
+                        if (j < M && k < M && j <= k) out(j, k, acc[a][b]);
+                    }
+            }
+        }
+    __syncthreads();
 }
 
 __device__ inline void refresh_out(const Slab &s, int M, int Kc)
@@ -281,28 +374,15 @@ __device__ inline void full_stat(Slab &s, GaussState &g, int N, int Kc, bool fir
 __device__ inline bool final_update(Slab &s, GaussState &g, int N, const Scratch &sc)
 {   // FinalUpdate*: H = beta PHI'PHI + diag(alpha), SIGMA = H^-1, Mu  (MainEff.c:1841-1921)
     const int M = g.M;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int npair = M * (M + 1) / 2;
-    for (int p = wid; p < npair; p += nw) {
-        // p -> (i <= j) by rows of the upper triangle
-        int j = (int)floor((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-        while ((j + 1) * (j + 2) / 2 <= p) j++;
-        while (j * (j + 1) / 2 > p) j--;
-        const int i = p - j * (j + 1) / 2;
-        const double *a = s.phi + (size_t)i * N, *b = s.phi + (size_t)j * N;
-        double z = 0;
-        for (int h = lane; h < N; h += 32) z = fma(a[h], b[h], z);
-        z = warp_sum(z);
-        if (lane == 0) {
-            double v = z * g.beta;
-            if (i == j) v += s.alpha[i];
-            s.H[j * M + i] = v; s.H[i * M + j] = v;
-        }
-    }
-    __syncthreads();
+    const double beta = g.beta;
+    gram_tiled(s.phi, N, M, nullptr, sc.sweep, [&](int i, int j, double z) {
+        double v = z * beta;
+        if (i == j) v += s.alpha[i];
+        s.H[j * M + i] = v; s.H[i * M + j] = v;
+    });
     for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) s.sigma[idx] = s.H[idx];
     __syncthreads();
-    const bool ok = spd_inverse_sweep(s.sigma, M, s.colk, sc);
+    const bool ok = spd_inverse_sweep(s.sigma, M, s.colk, sc, sc.sweep);
     posterior_mean(s, g, N);
     return ok;
 }

@@ -144,18 +144,23 @@ __global__ void lambda_max_kernel(const double *__restrict__ X, int N, int K, in
 
 // ---------------------------------------------------------------------------------------------
 // the persistent batched-fit kernel: one block = one fit at a time, fits pulled from a queue
-constexpr int FIT_THREADS = 256;
+constexpr int FIT_THREADS = 256;     // compile-time maximum (register budget: 2 x 256 or 4 x 128 threads per SM)
 
 template <bool EPIS, bool BINOMIAL>
 __global__ void __launch_bounds__(FIT_THREADS, 2)
 eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_tasks, int *queue, char *slabs,
                 size_t slab_stride, FitOutputs out)
 {
-    __shared__ __align__(32) double sV[SV_DOUBLES];      // double-buffered right-hand-side tiles of the contraction
+    // One shared buffer, used by phases that never overlap: the double-buffered right-hand-side tiles of
+    // the contraction (first SV_DOUBLES doubles) and the in-shared-memory sweep of small inverses.
+    constexpr int SWEEP_DOUBLES = SWEEP_SMEM_M * SWEEP_SMEM_M + 2 * SWEEP_SMEM_M;
+    constexpr int BUF_A = SWEEP_DOUBLES > SV_DOUBLES ? SWEEP_DOUBLES : SV_DOUBLES;
+    __shared__ __align__(32) double s_buf[BUF_A > GRAM_DOUBLES ? BUF_A : GRAM_DOUBLES];
+    double *sV = s_buf;
     __shared__ double red[66];
     __shared__ int redi[66];
     __shared__ int s_task;
-    Scratch sc{red, redi};
+    Scratch sc{red, redi, s_buf};
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_task = atomicAdd(queue, 1);
@@ -226,6 +231,7 @@ struct pareben_problem {
     double *d_flops = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int threads = 256;                   // threads per block actually launched
     double last_flops = 0, last_ms = 0; int last_launches = 0;
 
     template <class T> T *dalloc(size_t n)
@@ -358,12 +364,15 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         // resident blocks per SM of the kernel variant this problem will launch
         int per_sm = 1;
         {
+            // Block size: measured on B200 (config 2 / bundled Gaussian): 256 threads x 2 blocks per SM beats
+            // 128 x 4 (-5 % / -43 %) and 64 x 8 (-40 % / -70 %) (measured with an earlier build that had a run-time block size).
+            p->threads = FIT_THREADS;     // gram_tiled() maps 16 x 16 register blocks onto exactly 256 threads
             int occ = 0;
             cudaError_t e;
-            if (prior == PAREBEN_GAUSSIAN) e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, false>, FIT_THREADS, 0)
-                                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, false>, FIT_THREADS, 0);
-            else e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, true>, FIT_THREADS, 0)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, true>, FIT_THREADS, 0);
+            if (prior == PAREBEN_GAUSSIAN) e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, false>, p->threads, 0)
+                                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, false>, p->threads, 0);
+            else e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, true>, p->threads, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, true>, p->threads, 0);
             CU(e);
             per_sm = std::max(1, occ);
         }
@@ -462,11 +471,11 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
         const int grid = std::min(p->n_slabs, n_fits);
         CU(cudaEventRecord(p->ev0, p->stream));
         if (p->prior == PAREBEN_GAUSSIAN) {
-            if (p->epis) eben_fit_kernel<true, false><<<grid, FIT_THREADS, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
-            else eben_fit_kernel<false, false><<<grid, FIT_THREADS, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
+            if (p->epis) eben_fit_kernel<true, false><<<grid, p->threads, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
+            else eben_fit_kernel<false, false><<<grid, p->threads, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
         } else {
-            if (p->epis) eben_fit_kernel<true, true><<<grid, FIT_THREADS, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
-            else eben_fit_kernel<false, true><<<grid, FIT_THREADS, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
+            if (p->epis) eben_fit_kernel<true, true><<<grid, p->threads, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
+            else eben_fit_kernel<false, true><<<grid, p->threads, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
         }
         CU(cudaGetLastError());
         CU(cudaEventRecord(p->ev1, p->stream));

@@ -1,7 +1,7 @@
 """Small, short case for `ncu --set full`: a 296-fit slice of the config-2 grid (2 blocks per SM)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ.setdefault("PAREBEN_BLOCKS_PER_SM", "2")
+pass
 import numpy as np
 import pareben_b200 as pb
 
