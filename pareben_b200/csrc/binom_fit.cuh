@@ -50,6 +50,7 @@ __device__ inline double predictor_and_error(const Slab &s, int N, int M, const 
 template <bool EPIS>
 __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t, const Scratch &sc)
 {   // fEBCatPostMode*: Newton steps with step halving (NEmainEff.c:1808-2010, NeFull.c:998-1152)
+    PHASE(PH_IRLS_OTHER);      // includes the nested Gram/sweep phases (subtract them when reading the counters)
     const int M = b.M, T = blockDim.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
     double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2, *g = s.gamma, *dmu = s.u, *mun = s.tmp;
@@ -253,6 +254,7 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                     nu = s.block[iu];
                     selected = s.action[nu];
                     const double new_alpha = s.aroot[nu];
+                    { PHASE(PH_ACTIONS);
                     const bool need_sq = iu != n_update - 1;      // S/Q only matter to later actions of this block
                     if (selected == ACT_REEST || selected == ACT_DEL) {
                         const int a = s.amap[nu];
@@ -402,13 +404,15 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                         if (nu + 1 == initial) ini_removed = 1;                       // :744
                     }
                     __syncthreads();
-                    if (!need_sq) binom_full_stat<EPIS>(P, F, s, b, sV, sc);          // after the last action of the block (:749-762)
+                    }
+                    if (iu == n_update - 1) binom_full_stat<EPIS>(P, F, s, b, sV, sc);          // after the last action of the block (:749-762)
                 }
             }
             if (selected == ACT_TERM && ini_removed) last = 1;
             if ((i_iter == it_max && b.M == 2) || i_iter > it_max) last = 1;
             if (i_iter == it_max) selected = ACT_TERM;
             {   // global log-likelihood and its relative change (:782-801)
+                PHASE(PH_LOGLIK);
                 const int M = b.M;
                 double ll = 0;
                 for (int h = threadIdx.x; h < N; h += T) {

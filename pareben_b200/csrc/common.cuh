@@ -111,6 +111,22 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
 }
 
 // ------------------------------------------------------------------------------------------
+// Optional per-phase cycle accounting (compile with -DPAREBEN_PHASE_TIMING; experiments only).
+enum : int { PH_VFILL = 0, PH_CONTRACT, PH_QUAD, PH_GRAM, PH_SWEEP, PH_IRLS_OTHER, PH_DELTA_ML, PH_ACTIONS, PH_LOGLIK, PH_OTHER, PH_COUNT };
+#ifdef PAREBEN_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[PH_COUNT];
+__device__ unsigned long long g_phase_calls[PH_COUNT];
+struct PhaseTimer {
+    long long t0; int ph;
+    __device__ inline PhaseTimer(int p) : ph(p) { __syncthreads(); t0 = clock64(); if (threadIdx.x == 0) atomicAdd(&g_phase_calls[p], 1ULL); }
+    __device__ inline ~PhaseTimer() { __syncthreads(); if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[ph], (unsigned long long)(clock64() - t0)); }
+};
+#define PHASE(p) PhaseTimer phase_timer_##p(p)
+#else
+#define PHASE(p) do { } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------
 // block-level primitives.  `red` is a shared scratch of >= 33 doubles, `redi` >= 33 ints.
 struct Scratch { double *red; int *redi; double *sweep; /* SWEEP_SMEM_M^2 + 2*SWEEP_SMEM_M doubles, or null */ };
 

@@ -62,9 +62,13 @@ __device__ inline void contract(const XT *__restrict__ X, int N, int K, int Kc, 
     const int nchunk = (R + RC - 1) / RC, ntile = (N + TH - 1) / TH;
     const int Rp = nchunk * RC, Np = ntile * TH;
     __syncthreads();
+    {
+    PHASE(PH_VFILL);
     for (int r = 0; r < Rp; r++)                                  // h fastest: coalesced reads of the column-major sources
         for (int h = threadIdx.x; h < Np; h += T) V[(size_t)h * ldv + r] = (r < R && h < N) ? colval(r, h) : 0.0;
     __syncthreads();
+    }
+    PHASE(PH_CONTRACT);
     const int nstep = nchunk * ntile;
     for (int c0 = 0; c0 < Kc; c0 += T) {
         const int c = c0 + threadIdx.x;
@@ -139,6 +143,7 @@ template <class Emit>
 __device__ inline void quad_forms(const Slab &s, const double *sigma, double *sigp, int M, int Kc, const double *v,
                                   Emit emit)
 {
+    PHASE(PH_QUAD);
     const int T = blockDim.x;
     const int ldp = (M + 7) & ~7;
     for (int idx = threadIdx.x; idx < M * ldp; idx += T) {
@@ -226,16 +231,73 @@ __device__ inline bool sweep_core(double *a, int M, double *colbuf)
     return ok;
 }
 
+// Register-resident variant for M <= 64 and 256 threads: thread (warp w, lane l) owns rows {l, l+32}
+// x columns {w, w+8, ..., w+56} = 16 entries kept in registers across all M pivots; only the pivot
+// column travels through shared memory (2 x 64 doubles, double-buffered), one barrier per pivot.
+__device__ inline bool sweep_regs(double *a, int M, double *colbuf /* 128 doubles of shared memory */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double r[2][8];
+#pragma unroll
+    for (int ii = 0; ii < 2; ii++)
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            const int i = lane + 32 * ii, j = wid + 8 * jj;
+            r[ii][jj] = (i < M && j < M) ? a[(size_t)j * M + i] : 0.0;
+        }
+    double *cur = colbuf, *nxt = colbuf + 64;
+    __syncthreads();
+    if (wid == 0) {                                   // column 0 lives in warp 0 (jj = 0)
+        cur[lane] = r[0][0]; cur[lane + 32] = r[1][0];
+    }
+    __syncthreads();
+    bool ok = true;
+    PHASE(PH_OTHER);
+    for (int k = 0; k < M; k++) {
+        const double d = cur[k];
+        if (!(d > 0.0)) { ok = false; break; }
+        const double dinv = 1.0 / d;
+        const double ci0 = cur[lane], ci1 = cur[lane + 32];
+        const int kn = k + 1;
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            const int j = wid + 8 * jj;
+            const double cj = cur[j];
+#pragma unroll
+            for (int ii = 0; ii < 2; ii++) {
+                const int i = lane + 32 * ii;
+                const double ci = ii == 0 ? ci0 : ci1;
+                double v;
+                if (i == k && j == k) v = -dinv;
+                else if (i == k) v = cj * dinv;
+                else if (j == k) v = ci * dinv;
+                else v = r[ii][jj] - (ci * cj) * dinv;
+                r[ii][jj] = v;
+                if (j == kn) nxt[i] = v;
+            }
+        }
+        __syncthreads();
+        double *t = cur; cur = nxt; nxt = t;
+    }
+    if (ok) {
+#pragma unroll
+        for (int ii = 0; ii < 2; ii++)
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const int i = lane + 32 * ii, j = wid + 8 * jj;
+                if (i < M && j < M) a[(size_t)j * M + i] = -r[ii][jj];
+            }
+    }
+    return ok;
+}
+
 __device__ inline bool spd_inverse_sweep(double *a, int M, double *colk, const Scratch &sc, double *sm = nullptr)
 {
+    PHASE(PH_SWEEP);
     const int T = blockDim.x;
     bool ok;
-    if (sm && M <= SWEEP_SMEM_M) {
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < M * M; idx += T) sm[idx] = a[idx];
-        __syncthreads();
-        ok = sweep_core(sm, M, sm + SWEEP_SMEM_M * SWEEP_SMEM_M);
-        if (ok) for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -sm[idx];
+    if (sm && M <= SWEEP_SMEM_M && T == 256) {
+        ok = sweep_regs(a, M, sm);
     } else {
         ok = sweep_core(a, M, colk);          // colk: 2*(cap+1) doubles in the slab
         if (ok) for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -a[idx];
@@ -258,20 +320,31 @@ template <class Out>
 __device__ inline void gram_tiled(const double *__restrict__ phi, int N, int M, const double *__restrict__ w,
                                   double *sm, Out out)
 {
+    PHASE(PH_GRAM);
     double *sA = sm, *sB = sm + GR_ROWS * GR_LD;
     const int T = blockDim.x;
-    const int bj = threadIdx.x >> 4, bk = threadIdx.x & 15;      // 16 x 16 register blocks of 4 x 4 (first 256 threads)
-    const int npan = (M + GR_COLS - 1) / GR_COLS;
+    const int npan = (M + GR_COLS - 1) / GR_COLS, ntile = (N + GR_ROWS - 1) / GR_ROWS;
     for (int pj = 0; pj < npan; pj++)
         for (int pk = pj; pk < npan; pk++) {
             const int j0 = pj * GR_COLS, k0 = pk * GR_COLS;
-            const bool active = threadIdx.x < 256 && (pj != pk || bj <= bk) && j0 + 4 * bj < M && k0 + 4 * bk < M;
+            const int nbj = (min(GR_COLS, M - j0) + 3) >> 2, nbk = (min(GR_COLS, M - k0) + 3) >> 2;
+            // 4 x 4 register blocks needed in this panel: all of them off the diagonal, the upper triangle on it.
+            const int nblk = pj == pk ? nbj * (nbj + 1) / 2 : nbj * nbk;
+            // Threads left over are used to split the rows: block b is accumulated by `nsplit` threads,
+            // thread (b, s) taking row tiles s, s + nsplit, ...; partial sums are combined in fixed order.
+            const int nsplit = max(1, min(min(T, 256) / nblk, ntile));
+            const int blk = threadIdx.x % nblk, split = threadIdx.x / nblk;
+            const bool active = threadIdx.x < nblk * nsplit;
+            int bj = 0, bk = blk;
+            if (pj == pk) { int rem = blk; while (rem >= nbj - bj) { rem -= nbj - bj; bj++; } bk = bj + rem; }
+            else { bj = blk / nbk; bk = blk - bj * nbk; }
             double acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-            for (int h0 = 0; h0 < N; h0 += GR_ROWS) {
+            for (int ti = 0; ti < ntile; ti++) {
+                const int h0 = ti * GR_ROWS;
                 __syncthreads();
                 for (int idx = threadIdx.x; idx < GR_ROWS * GR_COLS; idx += T) {
                     const int hl = idx & (GR_ROWS - 1), cl = idx >> 5;         // consecutive threads -> consecutive rows
@@ -284,7 +357,7 @@ __device__ inline void gram_tiled(const double *__restrict__ phi, int N, int M, 
                     sA[hl * GR_LD + cl] = va; sB[hl * GR_LD + cl] = vb;
                 }
                 __syncthreads();
-                if (active) {
+                if (active && ti % nsplit == split) {
 #pragma unroll 4
                     for (int hl = 0; hl < GR_ROWS; hl++) {
                         const double2 *pa = reinterpret_cast<const double2 *>(sA + hl * GR_LD + 4 * bj);
@@ -298,14 +371,24 @@ __device__ inline void gram_tiled(const double *__restrict__ phi, int N, int M, 
                     }
                 }
             }
+            __syncthreads();                       // tiles are dead: reuse the buffer for the partial sums
             if (active) {
+                double *dst = sm + ((size_t)split * nblk + blk) * 16;
 #pragma unroll
                 for (int a = 0; a < 4; a++)
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int j = j0 + 4 * bj + a, k = k0 + 4 * bk + b;
-                        if (j < M && k < M && j <= k) out(j, k, acc[a][b]);
-                    }
+                    for (int b = 0; b < 4; b++) dst[a * 4 + b] = acc[a][b];
+            }
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < nblk * 16; idx += T) {
+                const int b2 = idx >> 4, e = idx & 15, a = e >> 2, b = e & 3;
+                double z = 0.0;
+                for (int sp = 0; sp < nsplit; sp++) z += sm[((size_t)sp * nblk + b2) * 16 + e];
+                int cj = 0, ck = b2;
+                if (pj == pk) { int rem = b2; while (rem >= nbj - cj) { rem -= nbj - cj; cj++; } ck = cj + rem; }
+                else { cj = b2 / nbk; ck = b2 - cj * nbk; }
+                const int j = j0 + 4 * cj + a, k = k0 + 4 * ck + b;
+                if (j < M && k < M && j <= k) out(j, k, z);
             }
         }
     __syncthreads();
@@ -395,6 +478,7 @@ __device__ inline Decision delta_ml(Slab &s, int M, int N, int Kc, double lambda
                                     double alpha_en, double residual, double var_y, int iter, int i_iter,
                                     const Scratch &sc)
 {   // fEBDeltaML* (MainEff.c:1372-1582; NeFull2.c:1227-1404; NEmainEff.c:2063-2238; NeFull.c:1775-1950)
+    PHASE(PH_DELTA_ML);
     const double l1 = lambda * alpha_en, l2 = lambda * (1 - alpha_en);
     int prio_add = 0, prio_del = 0;
     if (M < 10) { prio_add = 1; prio_del = 0; }

@@ -680,6 +680,20 @@ extern "C" int pareben_lambda_max(pareben_problem *p, double *lambda_max)
     return PAREBEN_OK;
 }
 
+// experiments only: cycles per phase summed over blocks (zeros unless built with -DPAREBEN_PHASE_TIMING)
+extern "C" int pareben_phase_cycles(unsigned long long *out, int reset)
+{
+#ifdef PAREBEN_PHASE_TIMING
+    if (out) { cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * PH_COUNT);
+               cudaMemcpyFromSymbol(out + PH_COUNT, g_phase_calls, sizeof(unsigned long long) * PH_COUNT); }
+    if (reset) { unsigned long long z[PH_COUNT] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z); cudaMemcpyToSymbol(g_phase_calls, z, sizeof z); }
+#else
+    if (out) for (int i = 0; i < 2 * PH_COUNT; i++) out[i] = 0;
+    (void)reset;
+#endif
+    return PH_COUNT;
+}
+
 extern "C" int pareben_last_counters(pareben_problem *p, double *flops, double *kernel_ms, int *launches)
 {
     if (!p) return fail(PAREBEN_EINVAL, "null problem");

@@ -1,0 +1,32 @@
+"""Experiments only: per-phase cycle totals of the fit kernel (needs libpareben_timing.so, built with
+-DPAREBEN_PHASE_TIMING).  usage: PAREBEN_LIB=pareben_b200/libpareben_timing.so python scripts/phase_timing.py [binomial|gaussian]"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import pareben_b200 as pb
+lib = pb.load()
+lib.pareben_phase_cycles.restype = ctypes.c_int
+lib.pareben_phase_cycles.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+names = ["vfill", "contract", "quad", "gram", "sweep", "irls(all, incl. gram+sweep)", "delta_ml", "actions", "loglik", "other"]
+g = np.load("tests/golden/inputs_bundled.npz")
+prior = sys.argv[1] if len(sys.argv) > 1 else "binomial"
+if prior == "binomial":
+    X, y, nf = g["BASISbinomial"].astype(float), g["yBinomial"].astype(float), 5
+else:
+    X, y, nf = g["BASIS"].astype(float), g["y"], 10
+folds = pb.AssignToFolds(X, nf); grid = pb.BuildGrid(X, y, nf)
+fold = np.tile(np.arange(1, nf + 1), 400); a = np.repeat(grid["alpha"], nf); l = np.repeat(grid["lambda"], nf)
+if prior != "binomial":
+    sel = np.arange(0, fold.size, 4); fold, a, l = fold[sel], a[sel], l[sel]
+with pb.Problem(X, y, folds, nf, False, prior) as p:
+    p.run_fits(fold, a, l)
+    buf = (ctypes.c_ulonglong * 32)()
+    lib.pareben_phase_cycles(buf, 1)
+    p.run_fits(fold, a, l)
+    fl, ms, _ = p.counters()
+    n = lib.pareben_phase_cycles(buf, 1)
+    cyc = np.array(buf[:n], dtype=float); calls = np.array(buf[n:2 * n], dtype=float)
+    total_block_cycles = ms * 1e-3 * 1.965e9 * 296
+    print(f"{prior}: kernel {ms:.1f} ms, {fold.size} fits; block-cycles available ~ {total_block_cycles:.3e}")
+    for nm, c, k in zip(names, cyc, calls):
+        print(f"  {nm:30s} {c:.3e}  {100*c/total_block_cycles:5.1f} % of block time   calls {k:.0f}  cycles/call {c/max(k,1):.0f}")
