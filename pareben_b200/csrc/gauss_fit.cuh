@@ -64,8 +64,15 @@ __device__ inline void contract(const XT *__restrict__ X, int N, int K, int Kc, 
     __syncthreads();
     {
     PHASE(PH_VFILL);
-    for (int r = 0; r < Rp; r++)                                  // h fastest: coalesced reads of the column-major sources
-        for (int h = threadIdx.x; h < Np; h += T) V[(size_t)h * ldv + r] = (r < R && h < N) ? colval(r, h) : 0.0;
+    // h fastest (coalesced reads of the column-major sources); four columns per pass so that four
+    // independent loads are in flight per thread
+    for (int r = 0; r < Rp; r += 4)
+        for (int h = threadIdx.x; h < Np; h += T) {
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = (r + q < R && h < N) ? colval(r + q, h) : 0.0;
+            *reinterpret_cast<double4 *>(V + (size_t)h * ldv + r) = make_double4(v[0], v[1], v[2], v[3]);
+        }
     __syncthreads();
     }
     PHASE(PH_CONTRACT);
@@ -252,28 +259,29 @@ __device__ inline bool sweep_regs(double *a, int M, double *colbuf /* 128 double
     }
     __syncthreads();
     bool ok = true;
-    PHASE(PH_OTHER);
     for (int k = 0; k < M; k++) {
         const double d = cur[k];
         if (!(d > 0.0)) { ok = false; break; }
-        const double dinv = 1.0 / d;
+        const double dinv = 1.0 / d, ndinv = -dinv;
         const double ci0 = cur[lane], ci1 = cur[lane + 32];
         const int kn = k + 1;
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
             const int j = wid + 8 * jj;
-            const double cj = cur[j];
+            if (j < M) {                                  // warp-uniform: whole columns beyond M are skipped
+                const double cj = cur[j];
 #pragma unroll
-            for (int ii = 0; ii < 2; ii++) {
-                const int i = lane + 32 * ii;
-                const double ci = ii == 0 ? ci0 : ci1;
-                double v;
-                if (i == k && j == k) v = -dinv;
-                else if (i == k) v = cj * dinv;
-                else if (j == k) v = ci * dinv;
-                else v = r[ii][jj] - (ci * cj) * dinv;
-                r[ii][jj] = v;
-                if (j == kn) nxt[i] = v;
+                for (int ii = 0; ii < 2; ii++) {
+                    const int i = lane + 32 * ii;
+                    const double ci = ii == 0 ? ci0 : ci1;
+                    double v;
+                    if (i == k && j == k) v = ndinv;
+                    else if (i == k) v = cj * dinv;
+                    else if (j == k) v = ci * dinv;
+                    else v = fma(ci * cj, ndinv, r[ii][jj]);      // (ci*cj) is symmetric in (i, j): the result stays exactly symmetric
+                    r[ii][jj] = v;
+                    if (j == kn) nxt[i] = v;
+                }
             }
         }
         __syncthreads();
