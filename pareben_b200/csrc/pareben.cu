@@ -281,9 +281,19 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
     try {
         p->device = device;
         CU(cudaSetDevice(device));
-        cudaDeviceProp prop;
-        CU(cudaGetDeviceProperties(&prop, device));
-        p->sm_count = prop.multiProcessorCount;
+        {   // cudaGetDeviceProperties costs milliseconds: ask once per device
+            static int sm_cache[64] = {0};
+            if (!sm_cache[device & 63]) CU(cudaDeviceGetAttribute(&sm_cache[device & 63], cudaDevAttrMultiProcessorCount, device));
+            p->sm_count = sm_cache[device & 63];
+        }
+        const bool timing = getenv("PAREBEN_TIMING") != nullptr;
+        auto tc0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+            if (!timing) return;
+            auto t = std::chrono::steady_clock::now();
+            fprintf(stderr, "[pareben]   create: %-28s %.2f ms\n", what, std::chrono::duration<double, std::milli>(t - tc0).count());
+            tc0 = t;
+        };
         p->n = n; p->k = k; p->epis = epis; p->prior = prior; p->n_folds = n_folds;
         p->kc = epis ? (int)((long long)k * (k + 1) / 2) : k;
         CU(cudaStreamCreate(&p->stream));
@@ -302,6 +312,7 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
             const double v = basis[i];
             if (!(v >= -127.0 && v <= 127.0) || v != (double)(int)v) small_int = false;
         }
+        lap("stream/events/h2d enqueue/scan");
         // row lists per fold: index 0 = all rows (only materialised when n_folds == 0)
         const int nf = n_folds;
         p->h_folds.assign(nf + 1, FoldData{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0});
@@ -345,6 +356,7 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
             }
         }
         CU(cudaGetLastError());
+        lap("per-fold layout (enqueue)");
         p->d_folds = p->dalloc<FoldData>(nf + 1);
         CU(cudaMemcpyAsync(p->d_folds, p->h_folds.data(), sizeof(FoldData) * (nf + 1), cudaMemcpyHostToDevice, p->stream));
 
@@ -359,26 +371,29 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
 
         // persistent grid: blocks per SM limited by memory for slabs
         p->slab_stride = slab_bytes(p->cap, p->nmax, p->kc);
-        size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
-        // resident blocks per SM of the kernel variant this problem will launch
+        // resident blocks per SM of the kernel variant this problem will launch (asked once per variant:
+        // the occupancy query, like cudaMemGetInfo below, costs up to tens of milliseconds)
         int per_sm = 1;
         {
             // Block size: measured on B200 (config 2 / bundled Gaussian): 256 threads x 2 blocks per SM beats
             // 128 x 4 (-5 % / -43 %) and 64 x 8 (-40 % / -70 %) (measured with an earlier build that had a run-time block size).
             p->threads = FIT_THREADS;     // gram_tiled() maps 16 x 16 register blocks onto exactly 256 threads
-            int occ = 0;
-            cudaError_t e;
-            if (prior == PAREBEN_GAUSSIAN) e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, false>, p->threads, 0)
-                                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, false>, p->threads, 0);
-            else e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, true>, p->threads, 0)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, true>, p->threads, 0);
-            CU(e);
+            static int occ_cache[4] = {0, 0, 0, 0};
+            int &occ = occ_cache[(prior == PAREBEN_BINOMIAL ? 2 : 0) + (epis ? 1 : 0)];
+            if (!occ) {
+                cudaError_t e;
+                if (prior == PAREBEN_GAUSSIAN) e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, false>, p->threads, 0)
+                                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, false>, p->threads, 0);
+                else e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, true>, p->threads, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, true>, p->threads, 0);
+                CU(e);
+            }
             per_sm = std::max(1, occ);
         }
         const char *env_bps = getenv("PAREBEN_BLOCKS_PER_SM");
         if (env_bps) per_sm = std::max(1, std::min(per_sm, atoi(env_bps)));
-        while (per_sm > 1 && (size_t)per_sm * p->sm_count * p->slab_stride > free_b / 2) per_sm--;
+        // First try the pool with the full-occupancy slab (the steady state of repeated CrossValidate calls);
+        // only a miss pays for cudaMemGetInfo and cudaMalloc.
         p->n_slabs = per_sm * p->sm_count;
         p->slab_total = (size_t)p->n_slabs * p->slab_stride;
         {
@@ -387,15 +402,23 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
             if (q) { p->d_slabs = (char *)q; p->slab_total = got; }
         }
         if (!p->d_slabs) {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            while (per_sm > 1 && (size_t)per_sm * p->sm_count * p->slab_stride > free_b / 2) per_sm--;
+            p->n_slabs = per_sm * p->sm_count;
+            while (p->n_slabs > 1 && (size_t)p->n_slabs * p->slab_stride > free_b - (free_b >> 3)) p->n_slabs /= 2;   // huge problems: fewer blocks
+            p->slab_total = (size_t)p->n_slabs * p->slab_stride;
             if (p->slab_total > free_b - (free_b >> 3))
                 throw std::make_pair((int)PAREBEN_ENOMEM, std::string("per-block work slabs do not fit in device memory; lower PAREBEN_BASIS_CAP"));
             void *q = nullptr;
             CU(cudaMalloc(&q, p->slab_total));
             p->d_slabs = (char *)q;
         }
+        lap("cap/occupancy/slab");
         p->d_queue = p->dalloc<int>(1);
         p->d_flops = p->dalloc<double>(1);
         CU(cudaStreamSynchronize(p->stream));
+        lap("final sync");
     } catch (std::pair<int, std::string> &e) {
         delete p;
         return fail(e.first, e.second);
