@@ -85,10 +85,12 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
             gj = warp_sum(gj);
             if (lane == 0) g[j] = gj - s.alpha[j - 1] * s.mu[j];
         }
-        gram_tiled(s.phi, N, M, w, sc.sweep, [&](int j, int k, double z) {
+        auto put = [&](int j, int k, double z) {
             if (j == k && j > 0) z += s.alpha[k - 1];
             s.H[k * M + j] = z; s.H[j * M + k] = z;
-        });
+        };
+        if (M <= PHIT_LD && blockDim.x == 256) gram_pipe(s.phit, N, M, w, sc.sweep, put);   // row-major copy, pipelined
+        else gram_tiled(s.phi, N, M, w, sc.sweep, put);
         for (int idx = threadIdx.x; idx < M * M; idx += T) s.sigma[idx] = s.H[idx];
         __syncthreads();
         if (!spd_inverse_sweep(s.sigma, M, s.colk, sc, sc.sweep)) b.status |= ST_NOT_PD;
@@ -183,7 +185,11 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
             for (int h = threadIdx.x; h < N; h += T) {
                 s.phi[h] = 1;
                 const double x = X[(size_t)h * K];
-                s.phi[(size_t)N + h] = EPIS ? x / sc0 : x * isc;              // NeFull.c:93 vs NEmainEff.c:1347-1350
+                const double p1 = EPIS ? x / sc0 : x * isc;                   // NeFull.c:93 vs NEmainEff.c:1347-1350
+                s.phi[(size_t)N + h] = p1;
+                double *pr = s.phit + (size_t)h * PHIT_LD;                    // row-major copy for the IRLS Gram matrix
+                pr[0] = 1; pr[1] = p1;
+                for (int j = 2; j < PHIT_LD; j++) pr[j] = 0;
             }
             __syncthreads();
             // least squares of [1 phi] on the pseudo-logits (dgelsy with rcond 1e-5, :1366-1370):
@@ -324,7 +330,10 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                                 for (int j = 0; j < M; j++) z = fma(s.sigma[i * M + j], s.tmp[j], z);
                                 s.u[i] = z;
                             }
-                            for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)M * N + h] = s.phinew[h];
+                            for (int h = threadIdx.x; h < N; h += T) {
+                                s.phi[(size_t)M * N + h] = s.phinew[h];
+                                if (M < PHIT_LD) s.phit[(size_t)h * PHIT_LD + M] = s.phinew[h];
+                            }
                             const double s_ii = 1.0 / (new_alpha + s.S_in[nu]);
                             const double mu_i = s_ii * s.Q_in[nu];
                             __syncthreads();
@@ -383,8 +392,14 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                             s.sigma_new[idx] = EPIS ? s.sigma[sjx * M + si] - sj[si] / sjj * sj[sjx]      // NeFull.c:1612
                                                     : s.sigma[sjx * M + si] - sj[si] * sj[sjx] / sjj;     // NEmainEff.c:1069
                         }
-                        if (j1 != lastj)
-                            for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)j1 * N + h] = s.phi[(size_t)lastj * N + h];
+                        for (int h = threadIdx.x; h < N; h += T) {
+                            if (j1 != lastj) {
+                                const double pv = s.phi[(size_t)lastj * N + h];
+                                s.phi[(size_t)j1 * N + h] = pv;
+                                if (j1 < PHIT_LD) s.phit[(size_t)h * PHIT_LD + j1] = pv;
+                            }
+                            if (lastj < PHIT_LD) s.phit[(size_t)h * PHIT_LD + lastj] = 0;     // vacated slot back to zero
+                        }
                         __syncthreads();
                         if (threadIdx.x == 0) {
                             if (j1 != lastj) {

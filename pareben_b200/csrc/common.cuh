@@ -62,6 +62,7 @@ struct Slab {
     double *sigma, *sigma_new, *H;      // cap*cap each
     double *phi;                        // nmax * cap, column-major (column j at phi + j*N)
     double *vbuf;                       // (nmax + 64) * vld(cap): right-hand sides of a contraction, row-major
+    double *phit;                       // nmax * PHIT_LD: row-major copy of the first PHIT_LD active columns (binomial IRLS)
     double *G;                          // cap * Kc: physical rows, row r at G + r*Kc
     double *xt, *S_in, *Q_in, *S_out, *Q_out, *dml, *aroot;   // Kc each
     double *t, *e, *phinew, *w1, *w2;   // nmax each
@@ -75,11 +76,12 @@ struct Slab {
 // 32-byte loads.
 __host__ __device__ inline size_t sig_elems(int cap) { return (((size_t)cap * (cap + 8)) + 3) & ~(size_t)3; }
 
+constexpr int PHIT_LD = 64;
 __host__ __device__ inline size_t vld(int cap) { return ((size_t)cap + 2 + 15) & ~(size_t)15; }   // leading dimension of vbuf
 
 __host__ __device__ inline size_t slab_doubles(int cap, int nmax, int Kc)
 {
-    return 3 * sig_elems(cap) + (size_t)nmax * cap + (size_t)(nmax + 64) * vld(cap) + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
+    return 3 * sig_elems(cap) + (size_t)nmax * cap + (size_t)(nmax + 64) * vld(cap) + (size_t)(nmax + 32) * PHIT_LD + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
            (size_t)7 * (cap + 1);
 }
 __host__ __device__ inline size_t slab_ints(int cap, int Kc) { return (size_t)2 * cap + (size_t)5 * Kc; }
@@ -97,6 +99,7 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
     s.sigma_new = d; d += sig_elems(cap);
     s.H = d; d += sig_elems(cap);
     s.vbuf = d; d += (size_t)(nmax + 64) * vld(cap);      // right after the 32-byte aligned matrices -> 32-byte aligned
+    s.phit = d; d += (size_t)(nmax + 32) * PHIT_LD;
     s.phi = d; d += (size_t)nmax * cap;
     s.G = d; d += (size_t)cap * Kc;
     s.xt = d; d += Kc; s.S_in = d; d += Kc; s.Q_in = d; d += Kc; s.S_out = d; d += Kc; s.Q_out = d; d += Kc;

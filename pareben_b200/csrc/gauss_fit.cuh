@@ -402,6 +402,91 @@ __device__ inline void gram_tiled(const double *__restrict__ phi, int N, int M, 
     __syncthreads();
 }
 
+// Pipelined Gram matrix for at most 64 active columns, from the ROW-major copy PHIt (leading dimension
+// PHIT_LD = 64):  H(j, k) = sum_h (phit[h][j] * w[h]) * phit[h][k],  j <= k.
+// Tiles of 32 rows (16 KB) are streamed with cp.async, double-buffered, so the copy of tile t+1
+// overlaps the FMAs of tile t and there is one barrier per tile (gram_tiled pays two barriers and
+// an exposed global load per tile).  Register blocks, row splitting and the fixed-order combination
+// of partial sums are as in gram_tiled.   smem: 2 * 32 * 64 + 64 doubles (w tiles).
+constexpr int GP_ROWS = 32;
+constexpr int GRAM_PIPE_DOUBLES = 2 * GP_ROWS * PHIT_LD + 2 * GP_ROWS;
+
+template <class Out>
+__device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, const double *__restrict__ w,
+                                 double *sm, Out out)
+{
+    PHASE(PH_GRAM);
+    const int T = blockDim.x;
+    double *tiles = sm, *wt = sm + 2 * GP_ROWS * PHIT_LD;
+    const int ntile = (N + GP_ROWS - 1) / GP_ROWS;
+    const int nb = (M + 3) >> 2, nblk = nb * (nb + 1) / 2;
+    const int nsplit = max(1, min(min(T, 256) / nblk, 8));
+    const int blk = threadIdx.x % nblk, split = threadIdx.x / nblk;
+    const bool active = threadIdx.x < nblk * nsplit;
+    int bj = 0, bk = blk;
+    { int rem = blk; while (rem >= nb - bj) { rem -= nb - bj; bj++; } bk = bj + rem; }
+    const int rps = (GP_ROWS + nsplit - 1) / nsplit;            // rows of a tile per split
+    auto stage = [&](int t) {
+        if (t < ntile) {
+            double *dst = tiles + (t & 1) * (GP_ROWS * PHIT_LD);
+            const int h0 = t * GP_ROWS;
+            for (int idx = threadIdx.x; idx < GP_ROWS * (PHIT_LD / 2); idx += T) {
+                const int hl = idx >> 5, q = idx & 31;          // 32 16-byte pieces per row
+                __pipeline_memcpy_async(dst + hl * PHIT_LD + 2 * q, phit + (size_t)min(h0 + hl, N - 1) * PHIT_LD + 2 * q, 16);
+            }
+            if (threadIdx.x < GP_ROWS) wt[(t & 1) * GP_ROWS + threadIdx.x] = (h0 + (int)threadIdx.x < N) ? (w ? w[h0 + threadIdx.x] : 1.0) : 0.0;
+        }
+        __pipeline_commit();
+    };
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+    __syncthreads();
+    stage(0);
+    for (int t = 0; t < ntile; t++) {
+        __pipeline_wait_prior(0);
+        __syncthreads();                                         // tile t visible; everyone finished tile t-1
+        stage(t + 1);
+        if (active) {
+            const double *tile = tiles + (t & 1) * (GP_ROWS * PHIT_LD), *wv = wt + (t & 1) * GP_ROWS;
+            const int hb = split * rps, he = min(hb + rps, GP_ROWS);
+#pragma unroll 2
+            for (int hl = hb; hl < he; hl++) {
+                const double4 a4 = *reinterpret_cast<const double4 *>(tile + hl * PHIT_LD + 4 * bj);
+                const double4 b4 = *reinterpret_cast<const double4 *>(tile + hl * PHIT_LD + 4 * bk);
+                const double ww = wv[hl];                        // rows past N carry weight 0
+                const double av[4] = {a4.x * ww, a4.y * ww, a4.z * ww, a4.w * ww}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+            }
+        }
+    }
+    __pipeline_wait_prior(0);
+    __syncthreads();                                             // tiles are dead: reuse the buffer for the partial sums
+    if (active) {
+        double *dst = sm + ((size_t)split * nblk + blk) * 16;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) dst[a * 4 + b] = acc[a][b];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nblk * 16; idx += T) {
+        const int b2 = idx >> 4, e = idx & 15, a = e >> 2, b = e & 3;
+        double z = 0.0;
+        for (int sp = 0; sp < nsplit; sp++) z += sm[((size_t)sp * nblk + b2) * 16 + e];
+        int cj = 0, ck = b2;
+        { int rem = b2; while (rem >= nb - cj) { rem -= nb - cj; cj++; } ck = cj + rem; }
+        const int j = 4 * cj + a, k = 4 * ck + b;
+        if (j < M && k < M && j <= k) out(j, k, z);
+    }
+    __syncthreads();
+}
+
 __device__ inline void refresh_out(const Slab &s, int M, int Kc)
 {   // S_out/Q_out = S_in/Q_in, with the in-model correction (MainEff.c:664-671, 1320-1338)
     for (int c = threadIdx.x; c < Kc; c += blockDim.x) {

@@ -155,7 +155,8 @@ eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_t
     // the contraction (first SV_DOUBLES doubles) and the in-shared-memory sweep of small inverses.
     constexpr int SWEEP_DOUBLES = SWEEP_SMEM_M * SWEEP_SMEM_M + 2 * SWEEP_SMEM_M;
     constexpr int BUF_A = SWEEP_DOUBLES > SV_DOUBLES ? SWEEP_DOUBLES : SV_DOUBLES;
-    __shared__ __align__(32) double s_buf[BUF_A > GRAM_DOUBLES ? BUF_A : GRAM_DOUBLES];
+    constexpr int BUF_B = BUF_A > GRAM_DOUBLES ? BUF_A : GRAM_DOUBLES;
+    __shared__ __align__(32) double s_buf[BUF_B > GRAM_PIPE_DOUBLES ? BUF_B : GRAM_PIPE_DOUBLES];
     double *sV = s_buf;
     __shared__ double red[66];
     __shared__ int redi[66];
