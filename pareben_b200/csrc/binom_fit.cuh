@@ -152,7 +152,7 @@ __device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab
             else if (r == 1) s.Q_in[c] = acc;
             else s.G[(size_t)s.grow[r - 2] * Kc + c] = acc / scale[c];
         }, s.vbuf, (int)vld(P.cap), sV, true);
-    quad_forms(s, s.sigma, s.sigma_new, M, Kc, nullptr, [&](int c, double quad, double) {
+    quad_forms(s, s.sigma, s.sigma_new, M, Kc, nullptr, sc.sweep, [&](int c, double quad, double) {
         const double sc_c = scale[c];
         s.S_in[c] = s.S_in[c] / (sc_c * sc_c) - quad;
         s.Q_in[c] = s.Q_in[c] / sc_c;

@@ -147,40 +147,65 @@ __device__ inline void contract_x(const FoldData &F, int K, int Kc, int R, ColVa
 // thread reads 8 consecutive entries of a row with two 32-byte loads; z_p accumulates over j in
 // ascending order and quad over p in ascending order, as the reference's loops do.
 template <class Emit>
-__device__ inline void quad_forms(const Slab &s, const double *sigma, double *sigp, int M, int Kc, const double *v,
-                                  Emit emit)
+__device__ inline void quad_forms(const Slab &s, const double *sigma, double *sigp_global, int M, int Kc, const double *v,
+                                  double *smem /* >= 4096 + 1040 doubles */, Emit emit)
 {
     PHASE(PH_QUAD);
     const int T = blockDim.x;
     const int ldp = (M + 7) & ~7;
+    // padded copy sigp[j][p] = SIGMA(p, j): in shared memory when it fits (M <= 64), else in the spare SIGMA buffer
+    double *sigp = (M * ldp <= 4096) ? smem : sigp_global;
+    size_t *rowoff = reinterpret_cast<size_t *>(smem + 4096);          // G row offsets: no dependent index load in the hot loop
+    __syncthreads();
     for (int idx = threadIdx.x; idx < M * ldp; idx += T) {
         const int j = idx / ldp, p = idx - j * ldp;
-        sigp[idx] = p < M ? sigma[p * M + j] : 0.0;           // sigp[j][p] = SIGMA(p, j)
+        sigp[idx] = p < M ? sigma[p * M + j] : 0.0;
     }
+    const bool off_smem = M <= 1040;
+    if (off_smem) for (int j = threadIdx.x; j < M; j += T) rowoff[j] = (size_t)s.grow[j] * Kc;
     __syncthreads();
-    for (int c = threadIdx.x; c < Kc; c += T) {
-        double quad = 0, lin = 0;
+    auto roff = [&](int j) -> size_t { return off_smem ? rowoff[j] : (size_t)s.grow[j] * Kc; };
+    // two candidates per thread share every SIGMA row fetched; four G rows are loaded ahead of their FMAs
+    for (int c0 = 0; c0 < Kc; c0 += 2 * T) {
+        const int ca = c0 + threadIdx.x, cb = ca + T;
+        const bool la = ca < Kc, lb = cb < Kc;
+        const int xa = la ? ca : 0, xb = lb ? cb : 0;
+        double quad_a = 0, lin_a = 0, quad_b = 0, lin_b = 0;
         for (int p0 = 0; p0 < M; p0 += 8) {
-            double z[8];
+            double za[8], zb[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) z[q] = 0.0;
-            for (int j = 0; j < M; j++) {
-                const double g = s.G[(size_t)s.grow[j] * Kc + c];
-                const double4 *row = reinterpret_cast<const double4 *>(sigp + (size_t)j * ldp + p0);
-                const double4 a = row[0], b = row[1];
-                z[0] = fma(g, a.x, z[0]); z[1] = fma(g, a.y, z[1]); z[2] = fma(g, a.z, z[2]); z[3] = fma(g, a.w, z[3]);
-                z[4] = fma(g, b.x, z[4]); z[5] = fma(g, b.y, z[5]); z[6] = fma(g, b.z, z[6]); z[7] = fma(g, b.w, z[7]);
+            for (int q = 0; q < 8; q++) { za[q] = 0.0; zb[q] = 0.0; }
+            for (int j = 0; j < M; j += 4) {
+                double ga[4], gb[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const size_t o = roff(min(j + u, M - 1));
+                    ga[u] = s.G[o + xa]; gb[u] = s.G[o + xb];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j + u < M) {
+                        const double4 *row = reinterpret_cast<const double4 *>(sigp + (size_t)(j + u) * ldp + p0);
+                        const double4 a = row[0], b = row[1];
+                        za[0] = fma(ga[u], a.x, za[0]); za[1] = fma(ga[u], a.y, za[1]); za[2] = fma(ga[u], a.z, za[2]); za[3] = fma(ga[u], a.w, za[3]);
+                        za[4] = fma(ga[u], b.x, za[4]); za[5] = fma(ga[u], b.y, za[5]); za[6] = fma(ga[u], b.z, za[6]); za[7] = fma(ga[u], b.w, za[7]);
+                        zb[0] = fma(gb[u], a.x, zb[0]); zb[1] = fma(gb[u], a.y, zb[1]); zb[2] = fma(gb[u], a.z, zb[2]); zb[3] = fma(gb[u], a.w, zb[3]);
+                        zb[4] = fma(gb[u], b.x, zb[4]); zb[5] = fma(gb[u], b.y, zb[5]); zb[6] = fma(gb[u], b.z, zb[6]); zb[7] = fma(gb[u], b.w, zb[7]);
+                    }
+                }
             }
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 if (p0 + q < M) {
-                    const double gp = s.G[(size_t)s.grow[p0 + q] * Kc + c];
-                    quad = fma(z[q], gp, quad);
-                    if (v) lin = fma(gp, v[p0 + q], lin);
+                    const size_t o = roff(p0 + q);
+                    const double gpa = s.G[o + xa], gpb = s.G[o + xb];
+                    quad_a = fma(za[q], gpa, quad_a); quad_b = fma(zb[q], gpb, quad_b);
+                    if (v) { lin_a = fma(gpa, v[p0 + q], lin_a); lin_b = fma(gpb, v[p0 + q], lin_b); }
                 }
             }
         }
-        emit(c, quad, lin);
+        if (la) emit(ca, quad_a, lin_a);
+        if (lb) emit(cb, quad_b, lin_b);
     }
     __syncthreads();
 }
@@ -539,7 +564,7 @@ __device__ inline void full_stat(Slab &s, GaussState &g, int N, int Kc, bool fir
     for (int i = 1 + threadIdx.x; i < M; i += blockDim.x) s.gamma[i] = 1.0 - s.sigma[i * M + i] * s.alpha[i];
     const double beta = g.beta;
     __syncthreads();
-    quad_forms(s, s.sigma, s.sigma_new, M, Kc, s.mu, [&](int c, double quad, double gm) {
+    quad_forms(s, s.sigma, s.sigma_new, M, Kc, s.mu, sc.sweep, [&](int c, double quad, double gm) {
         s.S_in[c] = beta - beta * quad * beta;
         s.Q_in[c] = beta * (s.xt[c] - gm);
     });

@@ -156,7 +156,9 @@ eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_t
     constexpr int SWEEP_DOUBLES = SWEEP_SMEM_M * SWEEP_SMEM_M + 2 * SWEEP_SMEM_M;
     constexpr int BUF_A = SWEEP_DOUBLES > SV_DOUBLES ? SWEEP_DOUBLES : SV_DOUBLES;
     constexpr int BUF_B = BUF_A > GRAM_DOUBLES ? BUF_A : GRAM_DOUBLES;
-    __shared__ __align__(32) double s_buf[BUF_B > GRAM_PIPE_DOUBLES ? BUF_B : GRAM_PIPE_DOUBLES];
+    constexpr int BUF_C = BUF_B > GRAM_PIPE_DOUBLES ? BUF_B : GRAM_PIPE_DOUBLES;
+    constexpr int QUAD_DOUBLES = 4096 + 1040;
+    __shared__ __align__(32) double s_buf[BUF_C > QUAD_DOUBLES ? BUF_C : QUAD_DOUBLES];
     double *sV = s_buf;
     __shared__ double red[66];
     __shared__ int redi[66];
