@@ -33,9 +33,11 @@ __device__ inline double predictor_and_error(const Slab &s, int N, int M, const 
                                              double *eta, double *yv, const Scratch &sc)
 {
     double err = 0;
+    const int LD = phi_ld(N);
     for (int h = threadIdx.x; h < N; h += blockDim.x) {
         double z = 0;
-        for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * N + h], mu[j], z);
+#pragma unroll 8
+        for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * LD + h], mu[j], z);
         eta[h] = z;
         const double y = 1 / (1 + exp(-z));
         yv[h] = y;
@@ -51,7 +53,7 @@ template <bool EPIS>
 __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t, const Scratch &sc)
 {   // fEBCatPostMode*: Newton steps with step halving (NEmainEff.c:1808-2010, NeFull.c:998-1152)
     PHASE(PH_IRLS_OTHER);      // includes the nested Gram/sweep phases (subtract them when reading the counters)
-    const int M = b.M, T = blockDim.x;
+    const int M = b.M, T = blockDim.x, LD = phi_ld(N);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
     double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2, *g = s.gamma, *dmu = s.u, *mun = s.tmp;
     double derr = predictor_and_error(s, N, M, s.mu, t, eta, yv, sc);
@@ -79,8 +81,9 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
         // as a tiled Gram matrix; column 0 of PHI is the intercept's all-ones column, so H(0, k) = sum w phi_k
         // and H(0, 0) = sum w come out of the same pass (:1887-1919).
         for (int j = 1 + wid; j < M; j += nw) {
-            const double *ph = s.phi + (size_t)j * N;
+            const double *ph = s.phi + (size_t)j * LD;
             double gj = 0;
+#pragma unroll 8
             for (int h = lane; h < N; h += 32) gj = fma(ph[h], e[h], gj);
             gj = warp_sum(gj);
             if (lane == 0) g[j] = gj - s.alpha[j - 1] * s.mu[j];
@@ -89,8 +92,7 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
             if (j == k && j > 0) z += s.alpha[k - 1];
             s.H[k * M + j] = z; s.H[j * M + k] = z;
         };
-        if (M <= PHIT_LD && blockDim.x == 256) gram_pipe(s.phit, N, M, w, sc.sweep, put);   // row-major copy, pipelined
-        else gram_tiled(s.phi, N, M, w, sc.sweep, put);
+        gram_mma(s.phi, N, LD, M, w, sc.sweep, put);
         for (int idx = threadIdx.x; idx < M * M; idx += T) s.sigma[idx] = s.H[idx];
         __syncthreads();
         if (!spd_inverse_sweep(s.sigma, M, s.colk, sc, sc.sweep)) b.status |= ST_NOT_PD;
@@ -127,14 +129,15 @@ template <bool EPIS>
 __device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab &s, BinomState &b, double *sV,
                                        const Scratch &sc)
 {   // fEBCatFullStat* (NEmainEff.c:1633-1803, NeFull.c:848-993)
-    const int N = F.ntr, K = P.K, Kc = P.Kc, T = blockDim.x;
+    const int N = F.ntr, K = P.K, Kc = P.Kc, T = blockDim.x, LD = phi_ld(N);
     const double *t = F.ytr, *scale = F.scale;
     post_mode<EPIS>(s, b, N, t, sc);
     const int M = b.M;
     double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2;
     for (int h = threadIdx.x; h < N; h += T) {
         double z = 0;
-        for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * N + h], s.mu[j], z);
+#pragma unroll 8
+        for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * LD + h], s.mu[j], z);
         eta[h] = z;
         const double y = 1 / (1 + exp(-z));
         yv[h] = y;
@@ -142,22 +145,19 @@ __device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab
     }
     __syncthreads();
     // One pass over the shared training matrix gives, per candidate c,
-    //   r = 0      bb = sum_h w[h] x_c[h]^2             (BBsquare, :1728-1729)
-    //   r = 1      ze = sum_h x_c[h] e[h]               (tempZE,  :1731-1732)
-    //   r = 2+p    G[p][c] = sum_h x_c[h] phi_p[h] w[h] / s_c   (BPvector, :1693-1702) -- kept as the action cache
-    contract_x<EPIS>(F, K, Kc, M + 2,
-        [&](int r, int h) { return r == 0 ? w[h] : (r == 1 ? e[h] : s.phi[(size_t)(r - 2) * N + h] * w[h]); },
-        [&](int r, int c, double acc) {
-            if (r == 0) s.S_in[c] = acc;
-            else if (r == 1) s.Q_in[c] = acc;
-            else s.G[(size_t)s.grow[r - 2] * Kc + c] = acc / scale[c];
-        }, s.vbuf, (int)vld(P.cap), sV, true);
+    //   bb = sum_h w[h] x_c[h]^2                        (BBsquare, :1728-1729)   -> S_in
+    //   ze = sum_h x_c[h] e[h]                          (tempZE,  :1731-1732)    -> Q_in
+    //   G[p][c] = sum_h x_c[h] phi_p[h] w[h] / s_c      (BPvector, :1693-1702)   -- kept as the action cache
+    contract_x<EPIS>(F, K, Kc, M, M,
+        [&](int r) -> const double * { return s.phi + (size_t)r * LD; },
+        [&](int r, bool &dv) -> double * { dv = true; return s.G + (size_t)s.grow[r] * Kc; },
+        sV, w, e, s.S_in, s.Q_in);
     quad_forms(s, s.sigma, s.sigma_new, M, Kc, nullptr, sc.sweep, [&](int c, double quad, double) {
         const double sc_c = scale[c];
         s.S_in[c] = s.S_in[c] / (sc_c * sc_c) - quad;
         s.Q_in[c] = s.Q_in[c] / sc_c;
     });
-    if (threadIdx.x == 0) b.flops += 2.0 * N * (double)Kc * (M + 2) + (double)Kc * (2.0 * M * M + M);
+    if (threadIdx.x == 0) b.flops += 2.0 * N * (double)Kc * (M + 2) + (double)Kc * (2.0 * M * M + M);     // SURVEY 8d model: w, e and the M columns
     refresh_out(s, M - 1, Kc);
 }
 
@@ -165,7 +165,7 @@ template <bool EPIS>
 __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v, Slab &s, double lambda,
                           double alpha_en, const FitTask &task, const FitOutputs &out, double *sV, const Scratch &sc)
 {
-    const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x;   // cap counts the intercept slot
+    const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x, LD = phi_ld(N);   // cap counts the intercept slot
     const double *X = F.Xtr, *t = F.ytr, *scale = F.scale;
     BinomState b; b.M = 2; b.n_unused = 0; b.status = 0; b.flops = 0;
     for (int j = threadIdx.x; j < cap + 1; j += T) { if (j < cap) s.grow[j] = j; s.alpha[j] = 0; s.mu[j] = 0; }
@@ -182,19 +182,17 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
             b.M = 2;
             if (threadIdx.x == 0) s.used[0] = 1;
             const double sc0 = scale[0], isc = 1 / sc0;
+            for (int h = N + threadIdx.x; h < LD; h += T) { s.phi[h] = 0; s.phi[(size_t)LD + h] = 0; }      // pad rows stay zero
             for (int h = threadIdx.x; h < N; h += T) {
                 s.phi[h] = 1;
                 const double x = X[(size_t)h * K];
                 const double p1 = EPIS ? x / sc0 : x * isc;                   // NeFull.c:93 vs NEmainEff.c:1347-1350
-                s.phi[(size_t)N + h] = p1;
-                double *pr = s.phit + (size_t)h * PHIT_LD;                    // row-major copy for the IRLS Gram matrix
-                pr[0] = 1; pr[1] = p1;
-                for (int j = 2; j < PHIT_LD; j++) pr[j] = 0;
+                s.phi[(size_t)LD + h] = p1;
             }
             __syncthreads();
             // least squares of [1 phi] on the pseudo-logits (dgelsy with rcond 1e-5, :1366-1370):
             // pivoted QR with the ones column leading (its norm sqrt(N) >= ||phi|| = 1)
-            const double *ph = s.phi + N;
+            const double *ph = s.phi + LD;
             double sphi = 0, sz = 0;
             for (int h = threadIdx.x; h < N; h += T) {
                 const double tp = 2 * t[h] - 1, pp = (tp * 0.9 + 1) / 2;
@@ -310,15 +308,16 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                             __syncthreads();
                             const int grow_new = s.grow[M];
                             if (need_sq) {
-                                contract_x<EPIS>(F, K, Kc, 1,
-                                    [&](int, int h) { return s.phinew[h] * s.w1[h]; },
-                                    [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, s.vbuf, (int)vld(cap), sV);
+                                contract_x<EPIS>(F, K, Kc, 1, 0,
+                                    [&](int) -> const double * { return s.phinew; },
+                                    [&](int, bool &dv) -> double * { dv = true; return s.G + (size_t)grow_new * Kc; }, sV, s.w1);
                             }
                             {   // tmp = PHI' (w o phi_new), one warp per active column
                                 const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
                                 for (int i = wid; i < M; i += nw) {
-                                    const double *p = s.phi + (size_t)i * N;
+                                    const double *p = s.phi + (size_t)i * LD;
                                     double z = 0;
+#pragma unroll 8
                                     for (int h = lane; h < N; h += 32) z = fma(p[h], s.w1[h] * s.phinew[h], z);
                                     z = warp_sum(z);
                                     if (lane == 0) s.tmp[i] = z;
@@ -330,9 +329,9 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                                 for (int j = 0; j < M; j++) z = fma(s.sigma[i * M + j], s.tmp[j], z);
                                 s.u[i] = z;
                             }
+                            for (int h = N + threadIdx.x; h < LD; h += T) s.phi[(size_t)M * LD + h] = 0;
                             for (int h = threadIdx.x; h < N; h += T) {
-                                s.phi[(size_t)M * N + h] = s.phinew[h];
-                                if (M < PHIT_LD) s.phit[(size_t)h * PHIT_LD + M] = s.phinew[h];
+                                s.phi[(size_t)M * LD + h] = s.phinew[h];
                             }
                             const double s_ii = 1.0 / (new_alpha + s.S_in[nu]);
                             const double mu_i = s_ii * s.Q_in[nu];
@@ -394,11 +393,8 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                         }
                         for (int h = threadIdx.x; h < N; h += T) {
                             if (j1 != lastj) {
-                                const double pv = s.phi[(size_t)lastj * N + h];
-                                s.phi[(size_t)j1 * N + h] = pv;
-                                if (j1 < PHIT_LD) s.phit[(size_t)h * PHIT_LD + j1] = pv;
+                                s.phi[(size_t)j1 * LD + h] = s.phi[(size_t)lastj * LD + h];
                             }
-                            if (lastj < PHIT_LD) s.phit[(size_t)h * PHIT_LD + lastj] = 0;     // vacated slot back to zero
                         }
                         __syncthreads();
                         if (threadIdx.x == 0) {
@@ -432,7 +428,8 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                 double ll = 0;
                 for (int h = threadIdx.x; h < N; h += T) {
                     double z = 0;
-                    for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * N + h], s.mu[j], z);
+#pragma unroll 8
+                    for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * LD + h], s.mu[j], z);
                     const double ez = exp(z);
                     ll += t[h] * log(ez / (1 + ez)) + (1 - t[h]) * log(1 / (1 + ez));
                 }

@@ -37,6 +37,11 @@ struct FoldData {
     const double *Xte;       // [nte][K] row-major held-out rows
     const double *yte;       // [nte]
     const double *scale;     // [Kc] column norms of the training rows (1 where the column is all zero)
+    // column-major (transposed) copies for the tensor-core contraction: column k at XT + k*ldt, rows zero-padded
+    // to ldt (a multiple of 32).  Exactly one of the two is non-null (int8 when Xtr8 is).
+    const int8_t *XT8;
+    const double *XTd;
+    int ldt;
     int ntr, nte;
 };
 
@@ -60,9 +65,7 @@ struct FitOutputs {
 // Per-block slab carved out of one big allocation.
 struct Slab {
     double *sigma, *sigma_new, *H;      // cap*cap each
-    double *phi;                        // nmax * cap, column-major (column j at phi + j*N)
-    double *vbuf;                       // (nmax + 64) * vld(cap): right-hand sides of a contraction, row-major
-    double *phit;                       // nmax * PHIT_LD: row-major copy of the first PHIT_LD active columns (binomial IRLS)
+    double *phi;                        // phi_ld(nmax) * cap, column-major (column j at phi + j*phi_ld(N), pad rows zero)
     double *G;                          // cap * Kc: physical rows, row r at G + r*Kc
     double *xt, *S_in, *Q_in, *S_out, *Q_out, *dml, *aroot;   // Kc each
     double *t, *e, *phinew, *w1, *w2;   // nmax each
@@ -71,17 +74,18 @@ struct Slab {
     int *unused, *upos, *amap, *action, *block;   // Kc each
 };
 
-// Each of the three cap x cap matrices is over-allocated to cap x (cap + 8), rounded to a multiple
-// of 4 doubles, so that either SIGMA buffer can hold the padded copy quad_forms() reads with
-// 32-byte loads.
-__host__ __device__ inline size_t sig_elems(int cap) { return (((size_t)cap * (cap + 8)) + 3) & ~(size_t)3; }
+// Each of the three cap x cap matrices is over-allocated to (cap + 32) x (cap + 8), rounded to a
+// multiple of 4 doubles, so that either SIGMA buffer can hold the zero-padded copy (rows to a multiple
+// of 32, columns to a multiple of 8) that quad_forms() streams into shared memory.
+__host__ __device__ inline size_t sig_elems(int cap) { return (((size_t)(cap + 32) * (cap + 8)) + 3) & ~(size_t)3; }
 
-constexpr int PHIT_LD = 64;
-__host__ __device__ inline size_t vld(int cap) { return ((size_t)cap + 2 + 15) & ~(size_t)15; }   // leading dimension of vbuf
+// leading dimension of the column-major active-column matrix PHI: rows padded to a multiple of 4 so that a lane
+// can fetch four consecutive rows of a column with 16-byte loads (the pad rows are kept at zero)
+__host__ __device__ inline int phi_ld(int n) { return (n + 3) & ~3; }
 
 __host__ __device__ inline size_t slab_doubles(int cap, int nmax, int Kc)
 {
-    return 3 * sig_elems(cap) + (size_t)nmax * cap + (size_t)(nmax + 64) * vld(cap) + (size_t)(nmax + 32) * PHIT_LD + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
+    return 3 * sig_elems(cap) + (size_t)phi_ld(nmax) * cap + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
            (size_t)7 * (cap + 1);
 }
 __host__ __device__ inline size_t slab_ints(int cap, int Kc) { return (size_t)2 * cap + (size_t)5 * Kc; }
@@ -98,9 +102,7 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
     s.sigma = d; d += sig_elems(cap);
     s.sigma_new = d; d += sig_elems(cap);
     s.H = d; d += sig_elems(cap);
-    s.vbuf = d; d += (size_t)(nmax + 64) * vld(cap);      // right after the 32-byte aligned matrices -> 32-byte aligned
-    s.phit = d; d += (size_t)(nmax + 32) * PHIT_LD;
-    s.phi = d; d += (size_t)nmax * cap;
+    s.phi = d; d += (size_t)phi_ld(nmax) * cap;
     s.G = d; d += (size_t)cap * Kc;
     s.xt = d; d += Kc; s.S_in = d; d += Kc; s.Q_in = d; d += Kc; s.S_out = d; d += Kc; s.Q_out = d; d += Kc;
     s.dml = d; d += Kc; s.aroot = d; d += Kc;
@@ -117,14 +119,18 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
 // Optional per-phase cycle accounting (compile with -DPAREBEN_PHASE_TIMING; experiments only).
 enum : int { PH_VFILL = 0, PH_CONTRACT, PH_QUAD, PH_GRAM, PH_SWEEP, PH_IRLS_OTHER, PH_DELTA_ML, PH_ACTIONS, PH_LOGLIK, PH_OTHER, PH_COUNT };
 #ifdef PAREBEN_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[PH_COUNT];
-__device__ unsigned long long g_phase_calls[PH_COUNT];
+static __device__ unsigned long long g_phase_cycles[PH_COUNT];
+static __device__ unsigned long long g_phase_calls[PH_COUNT];
 struct PhaseTimer {
     long long t0; int ph;
     __device__ inline PhaseTimer(int p) : ph(p) { __syncthreads(); t0 = clock64(); if (threadIdx.x == 0) atomicAdd(&g_phase_calls[p], 1ULL); }
     __device__ inline ~PhaseTimer() { __syncthreads(); if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[ph], (unsigned long long)(clock64() - t0)); }
 };
 #define PHASE(p) PhaseTimer phase_timer_##p(p)
+constexpr int FIT_TRACE_MAX = 1 << 16;
+static __device__ unsigned long long g_fit_t0[FIT_TRACE_MAX], g_fit_t1[FIT_TRACE_MAX];   // %globaltimer (ns) per fit
+static __device__ int g_fit_block[FIT_TRACE_MAX];
+__device__ inline unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #else
 #define PHASE(p) do { } while (0)
 #endif
@@ -243,6 +249,14 @@ struct Cand {
     static __device__ inline double small_int_to_double(int v)
     {
         return __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)v)) - 4503601774854144.0;
+    }
+    static __device__ inline int sbyte(int w, int b) { return (int)(int8_t)((unsigned)w >> (8 * b)); }
+    // element b (0..3) of a 4-row packed word pair loaded from the transposed int8 matrix
+    __device__ inline double from_words(int wi, int wj, int b) const
+    {
+        int v = sbyte(wi, b);
+        if (EPIS && i != j) v *= sbyte(wj, b);
+        return small_int_to_double(v);
     }
     __device__ inline double at(const int8_t *Xrow) const      // exact: |x| <= 127, products <= 2^14
     {

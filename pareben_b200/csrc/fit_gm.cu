@@ -1,0 +1,3 @@
+// fit_gm.cu -- eben_fit_kernel<EPIS=false, BINOMIAL=false> and its launcher (see fit_kernel.cuh).
+#include "fit_kernel.cuh"
+PAREBEN_DEFINE_VARIANT(gm, false, false)

@@ -25,187 +25,489 @@ struct GaussState {
 
 // ---- contraction: out(r, c) = sum_h x_c[h] * V_r[h]  for r in [0,R), c in [0,Kc) -------------
 // The right-hand sides are first written to a row-major buffer V[h][r] in global memory (leading
-// dimension ldv; rows zero-padded to a multiple of TH, columns to a multiple of RC).  Tiles of
-// TH rows x RC columns are then streamed into shared memory with cp.async, double-buffered, so the
-// copy of tile s+1 overlaps the FMAs of tile s and there is ONE barrier per tile.  Every thread
-// owns one candidate and keeps RC accumulators in registers: per row it needs one element of the
-// shared training matrix (int8 or f64, prefetched PF rows ahead) and RC values of V, broadcast
-// from shared memory with 32-byte loads.
-// Summation over rows is sequential in h for every (r, c): identical arithmetic for identical
-// columns, so exact duplicates tie exactly.
+// dimension ldv; rows and columns zero-padded), then streamed through shared memory with cp.async,
+// double-buffered, so the copy of tile s+1 overlaps the arithmetic of tile s and there is ONE
+// barrier per tile.  Two code paths share that staging:
+//
+//  * contract_mma (R > SIMT_R_MAX): FP64 tensor-core path, mma.sync.m8n8k4.f64 (DMMA).  A warp owns
+//    16 candidates (two 8-row A tiles) x up to 64 right-hand sides (eight 8-column B tiles) and
+//    keeps the 16 x 64 accumulator block in registers; per 4 rows it loads two A fragments (one
+//    element of the shared training matrix per lane, int8 or f64, prefetched a group ahead) and
+//    up to eight B fragments (conflict-free 8-byte shared loads) for up to sixteen DMMAs.  A thread-
+//    per-candidate DFMA loop needs one 8-byte shared operand per FMA and is capped at 25 % of the
+//    FP64 peak by the 128 B/clk shared-memory return path; the DMMA form needs 1/8 of that traffic.
+//  * contract_simt (R <= SIMT_R_MAX, the single new column of an add): one candidate per thread,
+//    RCS accumulators in registers.
+//
+// Summation over rows is in ascending h for every (r, c), with identical arithmetic for every
+// candidate, so exact duplicate columns tie exactly.
 //   colval(r, h)  value of right-hand side r at row h (the caller folds any row weight in)
 //   sq_first      when true, right-hand side 0 is contracted with x^2 instead of x
 //                 (the binomial sum_h w[h] x^2, NEmainEff.c:1728-1729)
-#ifndef PAREBEN_RC
-#define PAREBEN_RC 16
-#endif
-constexpr int RC = PAREBEN_RC;    // right-hand sides per register tile
-constexpr int TH = 64;            // rows per shared-memory tile
-constexpr int PF = 8;             // rows of X prefetched per group
-constexpr int SV_DOUBLES = 2 * TH * RC;
+constexpr int KT = 32;            // rows per shared-memory stage
+constexpr int NT_MAX = 4;         // 8-column B tiles per pass (32 right-hand sides): 16 x 32 accumulators = 32 registers, no spills
+constexpr int MT = 2;             // 8-candidate A tiles per warp
+constexpr int LDS_V = 68;         // leading dimension of a row-major staged tile (quadratic forms): == 4 (mod 16) doubles -> conflict-free B fragments
+constexpr int SIMT_R_MAX = 4;
+constexpr int RCS = 4;            // accumulators per thread in the SIMT path
+constexpr int PF = 8;             // rows of X prefetched per group (SIMT path)
+constexpr int FIT_T = 256;        // threads per block (the tile-production loops are unrolled for it)
 
-__device__ inline void stage_tile(double *dst, const double *__restrict__ V, int ldv, int h0, int r0)
-{   // TH rows x RC doubles, 16 bytes per cp.async
-    constexpr int CH = RC / 2;                 // 16-byte chunks per row
-    for (int idx = threadIdx.x; idx < TH * CH; idx += blockDim.x) {
-        const int h = idx / CH, q = idx - h * CH;
-        __pipeline_memcpy_async(dst + h * RC + 2 * q, V + (size_t)(h0 + h) * ldv + r0 + 2 * q, 16);
+__device__ inline void dmma(double &d0, double &d1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// KT rows x ncol doubles (ncol a multiple of 2) of V -> dst (leading dimension ldd), 16 bytes per cp.async.
+// PERM: within every group of 16 rows, row 4a + b is stored at position 4b + a, so that the lane that owns
+// four CONSECUTIVE rows of the A operand (one 32-bit load of the transposed int8 matrix) finds the matching
+// B rows at the positions the m8n8k4 fragment layout expects.
+template <bool PERM>
+__device__ inline void stage_tile(double *dst, int ldd, const double *__restrict__ V, int ldv, int h0, int r0, int ncol)
+{
+    const int ch = ncol >> 1;                  // 16-byte chunks per row
+    for (int idx = threadIdx.x; idx < KT * ch; idx += blockDim.x) {
+        const int h = idx / ch, q = idx - h * ch;
+        const int hp = PERM ? ((h & ~15) | ((h & 3) << 2) | ((h >> 2) & 3)) : h;
+        __pipeline_memcpy_async(dst + hp * ldd + 2 * q, V + (size_t)(h0 + h) * ldv + r0 + 2 * q, 16);
     }
     __pipeline_commit();
 }
 
-template <bool EPIS, class XT, class ColVal, class Store>
-__device__ inline void contract(const XT *__restrict__ X, int N, int K, int Kc, int R, ColVal colval,
-                                Store store, double *__restrict__ V, int ldv, double *sV, bool sq_first = false)
+// One pass over the rows for NT 8-column tiles of right-hand sides starting at column r0, all candidates.
+//   col(r)      base pointer of right-hand side r: N doubles, contiguous in the row index.  `n_aligned` of the
+//               leading columns (the active columns of PHI: 16-byte aligned, pad rows zero) are copied with
+//               16-byte cp.async, the rest (plain vectors) with 8-byte copies; rows >= N are zero-filled.
+//   wv, ev      binomial only (else null): row weights w[h] and residuals e[h].  The A operand is then x*w and
+//               two more sums per candidate ride along on the CUDA cores: bb = sum_h w x^2 and ze = sum_h x e.
+//   dest(r, div)  destination row of right-hand side r (element c at dest[c]); div = divide by scale[c]
+// Stages of KT rows are streamed through an NSTG-deep cp.async ring (no registers, the copies of two later
+// stages are in flight while one is consumed; one barrier per stage).  Tiles are stored column-major with
+// leading dimension LDS_C == 4 (mod 16) doubles, which makes the B-fragment loads bank-conflict free.
+constexpr int NSTG = 3;
+constexpr int LDS_C = KT + 4;
+constexpr int STAGE_DOUBLES = 8 * NT_MAX * LDS_C + 2 * KT;       // tile + w + e
+constexpr int SV_DOUBLES = NSTG * STAGE_DOUBLES;
+
+template <int NT, bool EPIS, class Col, class Dest>
+__device__ inline void mma_pass(const FoldData &F, int K, int Kc, int R, int r0, int n_aligned, Col col, Dest dest, double *sV,
+                                const double *__restrict__ wv, const double *__restrict__ ev, double *bb_out, double *ze_out)
 {
+    const int N = F.ntr, ldt = F.ldt;
+    const int8_t *__restrict__ X8 = F.XT8;
+    const double *__restrict__ Xd = F.XTd;
     const int T = blockDim.x;
-    const int nchunk = (R + RC - 1) / RC, ntile = (N + TH - 1) / TH;
-    const int Rp = nchunk * RC, Np = ntile * TH;
-    __syncthreads();
-    {
-    PHASE(PH_VFILL);
-    // h fastest (coalesced reads of the column-major sources); four columns per pass so that four
-    // independent loads are in flight per thread
-    for (int r = 0; r < Rp; r += 4)
-        for (int h = threadIdx.x; h < Np; h += T) {
-            double v[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = (r + q < R && h < N) ? colval(r + q, h) : 0.0;
-            *reinterpret_cast<double4 *>(V + (size_t)h * ldv + r) = make_double4(v[0], v[1], v[2], v[3]);
-        }
-    __syncthreads();
-    }
-    PHASE(PH_CONTRACT);
-    const int nstep = nchunk * ntile;
-    for (int c0 = 0; c0 < Kc; c0 += T) {
-        const int c = c0 + threadIdx.x;
-        const bool live = c < Kc;
-        Cand<EPIS> cd(live ? c : 0, K);
-        double acc[RC];
-#pragma unroll
-        for (int r = 0; r < RC; r++) acc[r] = 0.0;
-        stage_tile(sV, V, ldv, 0, 0);
-        __pipeline_wait_prior(0);
-        __syncthreads();
-        for (int st = 0; st < nstep; st++) {
-            const int chunk = st / ntile, tile = st - chunk * ntile;
-            const int r0 = chunk * RC, h0 = tile * TH;
-            const double *buf = sV + (st & 1) * (TH * RC);
-            if (st + 1 < nstep) {                                   // next tile in flight while this one is consumed
-                const int c2 = (st + 1) / ntile, t2 = (st + 1) - c2 * ntile;
-                stage_tile(sV + ((st + 1) & 1) * (TH * RC), V, ldv, t2 * TH, c2 * RC);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    const int gm = lane >> 2, gk = lane & 3;                  // fragment coordinates of this lane
+    const int nstage = (N + KT - 1) / KT, Np = nstage * KT;
+    const int n_mtile = (Kc + 7) >> 3;
+    const int per_round = nw * MT;
+    const int nround = (n_mtile + per_round - 1) / per_round;
+    const bool weighted = wv != nullptr;
+    const int ncol = min(8 * NT, R - r0);                     // live columns of this pass (the rest of the tile is zeroed once)
+    auto issue_stage = [&](int st) {
+        if (st < nstage) {
+            double *dst = sV + (st % NSTG) * STAGE_DOUBLES;
+            const int h0 = st * KT;
+            // aligned columns: KT/2 16-byte chunks each
+            const int na = max(0, min(ncol, n_aligned - r0));
+            for (int idx = threadIdx.x; idx < na * (KT / 2); idx += T) {
+                const int c = idx / (KT / 2), q = idx - c * (KT / 2), h = h0 + 2 * q;
+                const double *src = col(r0 + c);
+                __pipeline_memcpy_async(dst + c * LDS_C + 2 * q, src + min(h, N - 1 & ~1), 16, h < N ? 0 : 16);
             }
+            // plain vectors: 8-byte copies
+            for (int idx = threadIdx.x; idx < (ncol - na) * KT; idx += T) {
+                const int c = na + idx / KT, q = idx & (KT - 1), h = h0 + q;
+                const double *src = col(r0 + c);
+                __pipeline_memcpy_async(dst + c * LDS_C + q, src + min(h, N - 1), 8, h < N ? 0 : 8);
+            }
+            if (weighted) {
+                double *wd = dst + 8 * NT_MAX * LDS_C;
+                for (int idx = threadIdx.x; idx < 2 * KT; idx += T) {
+                    const int q = idx & (KT - 1), h = h0 + q;
+                    __pipeline_memcpy_async(wd + idx, (idx < KT ? wv : ev) + min(h, N - 1), 8, h < N ? 0 : 8);
+                }
+            }
+        }
+        __pipeline_commit();
+    };
+    // columns past the last live one are read by the fragment loads of the final 8-column tile: zero them once
+    for (int idx = threadIdx.x; idx < NSTG * (8 * NT - ncol) * KT; idx += T) {
+        const int sgi = idx / ((8 * NT - ncol) * KT), rem = idx - sgi * ((8 * NT - ncol) * KT);
+        sV[sgi * STAGE_DOUBLES + (ncol + rem / KT) * LDS_C + (rem & (KT - 1))] = 0.0;
+    }
+    for (int rd = 0; rd < nround; rd++) {
+        // this warp's two tiles: mt0 and mt0 + nw, so that a short last round is spread over all warps
+        const int mt0 = rd * per_round + wid;
+        const bool live = mt0 < n_mtile;
+        Cand<EPIS> cd0(min(mt0 * 8 + gm, Kc - 1), K), cd1(min((mt0 + nw) * 8 + gm, Kc - 1), K);
+        double acc[MT][NT][2];
+#pragma unroll
+        for (int t = 0; t < MT; t++)
+#pragma unroll
+            for (int n = 0; n < NT; n++) { acc[t][n][0] = 0.0; acc[t][n][1] = 0.0; }
+        double bb0 = 0.0, bb1 = 0.0, ze0 = 0.0, ze1 = 0.0;
+        // A fragments of one group of 16 rows.  The transposed training matrix is stored with the rows of every
+        // group permuted (physical position 4a + b holds row 4b + a), so the 32-bit word (or the four doubles) at
+        // positions 4*gk .. 4*gk+3 holds rows gk, gk+4, gk+8, gk+12: exactly this lane's element of the four k-steps.
+        // int8: the raw words of the next two groups sit in a two-slot ring (slot = group parity, static indices, no
+        // register moves); a slot is converted to doubles when its group becomes current and refilled at once with the
+        // group two ahead, so every load has two groups of DMMAs (>= 1000 cycles) to land.  f64: loaded one group ahead.
+        double xv[MT][4];
+        int wn[2][MT][2];
+        auto fetch8 = [&](int slot, int grp) {
+            const int h = min(16 * grp, Np - 16) + 4 * gk;
+            wn[slot][0][0] = *reinterpret_cast<const int *>(X8 + (size_t)cd0.i * ldt + h);
+            wn[slot][1][0] = *reinterpret_cast<const int *>(X8 + (size_t)cd1.i * ldt + h);
+            if (EPIS) {
+                wn[slot][0][1] = *reinterpret_cast<const int *>(X8 + (size_t)cd0.j * ldt + h);
+                wn[slot][1][1] = *reinterpret_cast<const int *>(X8 + (size_t)cd1.j * ldt + h);
+            }
+        };
+        // make group `grp` current (xv), then start the loads of group grp + 2 into the slot just freed
+        auto advance = [&](int slot, int grp) {
+            if (X8) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    xv[0][ks] = cd0.from_words(wn[slot][0][0], EPIS ? wn[slot][0][1] : 0, ks);
+                    xv[1][ks] = cd1.from_words(wn[slot][1][0], EPIS ? wn[slot][1][1] : 0, ks);
+                }
+                fetch8(slot, grp + 2);
+            } else {
+                const int h = min(16 * grp, Np - 16) + 4 * gk;
+                const double2 *p0 = reinterpret_cast<const double2 *>(Xd + (size_t)cd0.i * ldt + h);
+                const double2 *p1 = reinterpret_cast<const double2 *>(Xd + (size_t)cd1.i * ldt + h);
+                const double2 a = p0[0], b = p0[1], c = p1[0], d = p1[1];
+                xv[0][0] = a.x; xv[0][1] = a.y; xv[0][2] = b.x; xv[0][3] = b.y;
+                xv[1][0] = c.x; xv[1][1] = c.y; xv[1][2] = d.x; xv[1][3] = d.y;
+                if (EPIS) {
+                    if (cd0.i != cd0.j) {
+                        const double2 *q0 = reinterpret_cast<const double2 *>(Xd + (size_t)cd0.j * ldt + h);
+                        const double2 e = q0[0], f = q0[1];
+                        xv[0][0] *= e.x; xv[0][1] *= e.y; xv[0][2] *= f.x; xv[0][3] *= f.y;
+                    }
+                    if (cd1.i != cd1.j) {
+                        const double2 *q1 = reinterpret_cast<const double2 *>(Xd + (size_t)cd1.j * ldt + h);
+                        const double2 e = q1[0], f = q1[1];
+                        xv[1][0] *= e.x; xv[1][1] *= e.y; xv[1][2] *= f.x; xv[1][3] *= f.y;
+                    }
+                }
+            }
+        };
+        __syncthreads();                                       // the ring is free (previous round / pass fully consumed)
+#pragma unroll
+        for (int d = 0; d < NSTG - 1; d++) issue_stage(d);
+        if (live) {
+            if (X8) { fetch8(0, 0); fetch8(1, 1); }
+            advance(0, 0);
+        }
+        for (int st = 0; st < nstage; st++) {
+            __pipeline_wait_prior(NSTG - 2);                   // stage st has landed (for this thread's copies)
+            __syncthreads();                                   // ... and for everyone's; stage st-1 is fully consumed
+            issue_stage(st + NSTG - 1);
+            const double *buf = sV + (st % NSTG) * STAGE_DOUBLES;
+            const double *wrow = buf + 8 * NT_MAX * LDS_C;
             if (live) {
-                const bool sq = sq_first && r0 == 0;
-                const int nh = min(TH, N - h0);
-                double xv[PF];
 #pragma unroll
-                for (int i = 0; i < PF; i++) xv[i] = cd.at(X + (size_t)min(h0 + i, N - 1) * K);
-                for (int hh = 0; hh < nh; hh += PF) {
-                    double xn[PF];
+                for (int g = 0; g < KT / 16; g++) {
 #pragma unroll
-                    for (int i = 0; i < PF; i++) xn[i] = cd.at(X + (size_t)min(h0 + hh + PF + i, N - 1) * K);
+                    for (int ks = 0; ks < 4; ks++) {
+                        const int hl = 16 * g + 4 * ks + gk;
+                        const double *bcol = buf + gm * LDS_C + hl;
+                        double a0 = xv[0][ks], a1 = xv[1][ks];
+                        double b[NT];
 #pragma unroll
-                    for (int i = 0; i < PF; i++) {
-                        const double x = xv[i];
-                        const double4 *v4 = reinterpret_cast<const double4 *>(buf + (hh + i) * RC);
+                        for (int n = 0; n < NT; n++) b[n] = bcol[8 * n * LDS_C];
+                        if (weighted) {
+                            const double w = wrow[hl], e = wrow[KT + hl];
+                            bb0 = fma(a0 * a0, w, bb0); bb1 = fma(a1 * a1, w, bb1);
+                            ze0 = fma(a0, e, ze0); ze1 = fma(a1, e, ze1);
+                            a0 *= w; a1 *= w;
+                        }
 #pragma unroll
-                        for (int q = 0; q < RC / 4; q++) {
-                            const double4 a = v4[q];
-                            acc[4 * q + 0] = fma((q == 0 && sq) ? x * x : x, a.x, acc[4 * q + 0]);
-                            acc[4 * q + 1] = fma(x, a.y, acc[4 * q + 1]);
-                            acc[4 * q + 2] = fma(x, a.z, acc[4 * q + 2]);
-                            acc[4 * q + 3] = fma(x, a.w, acc[4 * q + 3]);
+                        for (int n = 0; n < NT; n++) {
+                            dmma(acc[0][n][0], acc[0][n][1], a0, b[n]);
+                            dmma(acc[1][n][0], acc[1][n][1], a1, b[n]);
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < PF; i++) xv[i] = xn[i];
-                }
-                if (tile == ntile - 1) {
-#pragma unroll
-                    for (int r = 0; r < RC; r++) { if (r0 + r < R) store(r0 + r, c, acc[r]); acc[r] = 0.0; }
+                    advance((g + 1) & 1, st * (KT / 16) + g + 1);      // KT / 16 == 2: the slot index is a compile-time constant
                 }
             }
-            __pipeline_wait_prior(0);
-            __syncthreads();
+        }
+        __pipeline_wait_prior(0);
+        if (live) {
+            if (weighted && r0 == 0) {
+                bb0 += __shfl_xor_sync(0xffffffffu, bb0, 1); bb0 += __shfl_xor_sync(0xffffffffu, bb0, 2);
+                bb1 += __shfl_xor_sync(0xffffffffu, bb1, 1); bb1 += __shfl_xor_sync(0xffffffffu, bb1, 2);
+                ze0 += __shfl_xor_sync(0xffffffffu, ze0, 1); ze0 += __shfl_xor_sync(0xffffffffu, ze0, 2);
+                ze1 += __shfl_xor_sync(0xffffffffu, ze1, 1); ze1 += __shfl_xor_sync(0xffffffffu, ze1, 2);
+                if (gk == 0) {
+                    const int ca = mt0 * 8 + gm, cb = (mt0 + nw) * 8 + gm;
+                    if (ca < Kc) { bb_out[ca] = bb0; ze_out[ca] = ze0; }
+                    if (cb < Kc) { bb_out[cb] = bb1; ze_out[cb] = ze1; }
+                }
+            }
+            // destination rows first (their look-ups are independent loads), then divide and store
+            double *rowp[NT][2];
+            bool rdiv[NT][2];
+#pragma unroll
+            for (int n = 0; n < NT; n++)
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int r = r0 + 8 * n + 2 * gk + i;
+                    rdiv[n][i] = false;
+                    rowp[n][i] = r < R ? dest(r, rdiv[n][i]) : nullptr;
+                }
+#pragma unroll
+            for (int t = 0; t < MT; t++) {
+                const int c = (mt0 + t * nw) * 8 + gm;
+                if (c < Kc) {
+                    const double sc = F.scale[c];
+#pragma unroll
+                    for (int n = 0; n < NT; n++)
+#pragma unroll
+                        for (int i = 0; i < 2; i++)
+                            if (rowp[n][i]) rowp[n][i][c] = rdiv[n][i] ? acc[t][n][i] / sc : acc[t][n][i];
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <bool EPIS, class Col, class Dest>
+__device__ inline void contract_mma(const FoldData &F, int K, int Kc, int R, int n_aligned, Col col, Dest dest, double *sV,
+                                    const double *wv = nullptr, const double *ev = nullptr, double *bb_out = nullptr, double *ze_out = nullptr)
+{
+    const int Rp = (R + 7) & ~7;
+    __syncthreads();
+    PHASE(PH_CONTRACT);
+    for (int r0 = 0; r0 < Rp; r0 += 8 * NT_MAX) {
+        const int nt = min(NT_MAX, (Rp - r0) >> 3);
+        switch (nt) {
+        case 1: mma_pass<1, EPIS>(F, K, Kc, R, r0, n_aligned, col, dest, sV, wv, ev, bb_out, ze_out); break;
+        case 2: mma_pass<2, EPIS>(F, K, Kc, R, r0, n_aligned, col, dest, sV, wv, ev, bb_out, ze_out); break;
+        case 3: mma_pass<3, EPIS>(F, K, Kc, R, r0, n_aligned, col, dest, sV, wv, ev, bb_out, ze_out); break;
+        default: mma_pass<4, EPIS>(F, K, Kc, R, r0, n_aligned, col, dest, sV, wv, ev, bb_out, ze_out); break;
         }
     }
 }
 
-// Dispatch on the storage type of the shared training matrix (int8 genotype codes when available).
-template <bool EPIS, class ColVal, class Store>
-__device__ inline void contract_x(const FoldData &F, int K, int Kc, int R, ColVal colval, Store store, double *V, int ldv,
-                                  double *sV, bool sq_first = false)
+// R <= RCS right-hand sides (the single new column of an add): one candidate per thread, the right-hand
+// sides of up to SIMT_ROWS rows held in shared memory (row-major, RCS per row) and broadcast with 32-byte loads.
+constexpr int SIMT_ROWS = (2 * KT * LDS_V) / RCS;
+
+template <bool EPIS, class XT, class ColVal, class Dest>
+__device__ inline void contract_simt(const XT *__restrict__ X, int N, int K, int Kc, int R, ColVal colval,
+                                     Dest dest, const double *__restrict__ scale, double *sV, bool sq_first)
 {
-    if (F.Xtr8) contract<EPIS, int8_t>(F.Xtr8, F.ntr, K, Kc, R, colval, store, V, ldv, sV, sq_first);
-    else contract<EPIS, double>(F.Xtr, F.ntr, K, Kc, R, colval, store, V, ldv, sV, sq_first);
+    const int T = blockDim.x;
+    __syncthreads();
+    PHASE(PH_CONTRACT);
+    for (int hb = 0; hb < N; hb += SIMT_ROWS) {
+        const int nh = min(SIMT_ROWS, N - hb);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nh * RCS; idx += T) {
+            const int h = idx % nh, r = idx / nh;                         // row fastest: coalesced reads of the sources
+            sV[h * RCS + r] = r < R ? colval(r, hb + h) : 0.0;
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < Kc; c0 += T) {
+            const int c = c0 + threadIdx.x;
+            if (c >= Kc) continue;
+            Cand<EPIS> cd(c, K);
+            double acc[RCS];
+#pragma unroll
+            for (int r = 0; r < RCS; r++) acc[r] = 0.0;
+            double xv[PF];
+#pragma unroll
+            for (int i = 0; i < PF; i++) xv[i] = cd.at(X + (size_t)min(hb + i, N - 1) * K);
+            for (int hh = 0; hh < nh; hh += PF) {
+                double xn[PF];
+#pragma unroll
+                for (int i = 0; i < PF; i++) xn[i] = cd.at(X + (size_t)min(hb + hh + PF + i, N - 1) * K);
+#pragma unroll
+                for (int i = 0; i < PF; i++) {
+                    if (hh + i < nh) {
+                        const double x = xv[i];
+                        const double4 a = *reinterpret_cast<const double4 *>(sV + (hh + i) * RCS);
+                        acc[0] = fma(sq_first ? x * x : x, a.x, acc[0]);
+                        acc[1] = fma(x, a.y, acc[1]);
+                        acc[2] = fma(x, a.z, acc[2]);
+                        acc[3] = fma(x, a.w, acc[3]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < PF; i++) xv[i] = xn[i];
+            }
+            const double sc = scale[c];
+#pragma unroll
+            for (int r = 0; r < RCS; r++) {
+                if (r < R) {
+                    bool dv = false;
+                    double *row = dest(r, dv);
+                    // row chunks after the first accumulate onto the stored partial sum (un-scaled until the last chunk)
+                    double v = acc[r];
+                    if (hb > 0) v += row[c];
+                    row[c] = (dv && hb + nh >= N) ? v / sc : v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Dispatch on the number of right-hand sides (and, in the SIMT path, on the storage type of the training matrix).
+//   col(r)        base pointer of right-hand side r (see mma_pass); the first n_aligned are 16-byte aligned columns
+//   dest(r, div)  destination row of right-hand side r; div set when the result is divided by the column norm
+//   wv            optional row weights folded into the product (binomial); the SIMT path applies them per row
+template <bool EPIS, class Col, class Dest>
+__device__ inline void contract_x(const FoldData &F, int K, int Kc, int R, int n_aligned, Col col, Dest dest, double *sV,
+                                  const double *wv = nullptr, const double *ev = nullptr, double *bb_out = nullptr, double *ze_out = nullptr)
+{
+    if (R <= SIMT_R_MAX && !bb_out) {
+        auto colval = [&](int r, int h) { const double v = col(r)[h]; return wv ? v * wv[h] : v; };
+        if (F.Xtr8) contract_simt<EPIS, int8_t>(F.Xtr8, F.ntr, K, Kc, R, colval, dest, F.scale, sV, false);
+        else contract_simt<EPIS, double>(F.Xtr, F.ntr, K, Kc, R, colval, dest, F.scale, sV, false);
+    } else {
+        contract_mma<EPIS>(F, K, Kc, R, n_aligned, col, dest, sV, wv, ev, bb_out, ze_out);
+    }
 }
 
 // Quadratic forms of the candidate cache against the active-set inverse:
 //   quad[c] = g_c' SIGMA g_c,  lin[c] = g_c' v      with g_c = G[:, c]   (FullStat*, MainEff.c:1291-1316)
-// SIGMA is first copied to a padded layout (leading dimension ldp, multiple of 8, in `sigp`) so a
-// thread reads 8 consecutive entries of a row with two 32-byte loads; z_p accumulates over j in
-// ascending order and quad over p in ascending order, as the reference's loops do.
-template <class Emit>
-__device__ inline void quad_forms(const Slab &s, const double *sigma, double *sigp_global, int M, int Kc, const double *v,
-                                  double *smem /* >= 4096 + 1040 doubles */, Emit emit)
+// Tensor-core form: Z = G' SIGMA is a (Kc x M) x (M x M) product -- A fragments are 8 candidates x 4 cache
+// rows read straight from G (through the row permutation), B fragments come from a zero-padded copy of
+// SIGMA in shared memory -- and quad[c] = sum_p Z[c][p] G[p][c] is folded into the accumulator epilogue.
+// For M <= 2*KT the padded SIGMA stays resident in shared memory for the whole call; larger matrices are
+// streamed through the same double buffer in 64-column chunks from a padded copy in the spare SIGMA buffer.
+// Every candidate goes through the identical sequence of operations (duplicate columns tie exactly).
+template <int NT>
+__device__ inline void quad_chunk(const double *__restrict__ G, const size_t *rowoff, const int *grow, int M, int Kc,
+                                  const double *__restrict__ sigp, int ldp, int p0, double *sV, bool resident,
+                                  bool live, int c0, int c1, const double *__restrict__ v, double (&q)[MT], double (&l)[MT])
 {
-    PHASE(PH_QUAD);
-    const int T = blockDim.x;
-    const int ldp = (M + 7) & ~7;
-    // padded copy sigp[j][p] = SIGMA(p, j): in shared memory when it fits (M <= 64), else in the spare SIGMA buffer
-    double *sigp = (M * ldp <= 4096) ? smem : sigp_global;
-    size_t *rowoff = reinterpret_cast<size_t *>(smem + 4096);          // G row offsets: no dependent index load in the hot loop
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < M * ldp; idx += T) {
-        const int j = idx / ldp, p = idx - j * ldp;
-        sigp[idx] = p < M ? sigma[p * M + j] : 0.0;
-    }
-    const bool off_smem = M <= 1040;
-    if (off_smem) for (int j = threadIdx.x; j < M; j += T) rowoff[j] = (size_t)s.grow[j] * Kc;
-    __syncthreads();
-    auto roff = [&](int j) -> size_t { return off_smem ? rowoff[j] : (size_t)s.grow[j] * Kc; };
-    // two candidates per thread share every SIGMA row fetched; four G rows are loaded ahead of their FMAs
-    for (int c0 = 0; c0 < Kc; c0 += 2 * T) {
-        const int ca = c0 + threadIdx.x, cb = ca + T;
-        const bool la = ca < Kc, lb = cb < Kc;
-        const int xa = la ? ca : 0, xb = lb ? cb : 0;
-        double quad_a = 0, lin_a = 0, quad_b = 0, lin_b = 0;
-        for (int p0 = 0; p0 < M; p0 += 8) {
-            double za[8], zb[8];
+    const int lane = threadIdx.x & 31;
+    const int gm = lane >> 2, gk = lane & 3;
+    const int nstage = (M + KT - 1) / KT;
+    auto roff = [&](int j) -> size_t { return rowoff ? rowoff[j] : (size_t)grow[j] * Kc; };
+    double acc[MT][NT][2];
 #pragma unroll
-            for (int q = 0; q < 8; q++) { za[q] = 0.0; zb[q] = 0.0; }
-            for (int j = 0; j < M; j += 4) {
-                double ga[4], gb[4];
+    for (int t = 0; t < MT; t++)
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const size_t o = roff(min(j + u, M - 1));
-                    ga[u] = s.G[o + xa]; gb[u] = s.G[o + xb];
-                }
+        for (int n = 0; n < NT; n++) { acc[t][n][0] = 0.0; acc[t][n][1] = 0.0; }
+    double xv[MT][4], xn[MT][4], xn2[MT][4];                // cache rows come from L2: two groups (32 rows) in flight
+    auto fetch = [&](double (&x)[MT][4], int jb) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (j + u < M) {
-                        const double4 *row = reinterpret_cast<const double4 *>(sigp + (size_t)(j + u) * ldp + p0);
-                        const double4 a = row[0], b = row[1];
-                        za[0] = fma(ga[u], a.x, za[0]); za[1] = fma(ga[u], a.y, za[1]); za[2] = fma(ga[u], a.z, za[2]); za[3] = fma(ga[u], a.w, za[3]);
-                        za[4] = fma(ga[u], b.x, za[4]); za[5] = fma(ga[u], b.y, za[5]); za[6] = fma(ga[u], b.z, za[6]); za[7] = fma(ga[u], b.w, za[7]);
-                        zb[0] = fma(gb[u], a.x, zb[0]); zb[1] = fma(gb[u], a.y, zb[1]); zb[2] = fma(gb[u], a.z, zb[2]); zb[3] = fma(gb[u], a.w, zb[3]);
-                        zb[4] = fma(gb[u], b.x, zb[4]); zb[5] = fma(gb[u], b.y, zb[5]); zb[6] = fma(gb[u], b.z, zb[6]); zb[7] = fma(gb[u], b.w, zb[7]);
+        for (int ks = 0; ks < 4; ks++) {
+            const size_t o = roff(min(jb + 4 * ks + gk, M - 1));
+            x[0][ks] = G[o + c0];
+            x[1][ks] = G[o + c1];
+        }
+    };
+    if (!resident) stage_tile<false>(sV, LDS_V, sigp, ldp, 0, p0, 8 * NT);
+    if (live) { fetch(xv, 0); fetch(xn, 16); }
+    if (!resident) { __pipeline_wait_prior(0); __syncthreads(); }
+    for (int st = 0; st < nstage; st++) {
+        const double *buf = sV + (st & 1) * (KT * LDS_V);
+        if (!resident && st + 1 < nstage) stage_tile<false>(sV + ((st + 1) & 1) * (KT * LDS_V), LDS_V, sigp, ldp, (st + 1) * KT, p0, 8 * NT);
+        if (live) {
+#pragma unroll
+            for (int g = 0; g < KT / 16; g++) {
+                if (st * KT + 16 * g < M) {                    // warp-uniform: groups past the last cache row are skipped
+                    fetch(xn2, st * KT + 16 * (g + 2));
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const double *brow = buf + (16 * g + 4 * ks + gk) * LDS_V + gm + (resident ? p0 : 0);   // the resident tile holds every column
+                        double b[NT];
+#pragma unroll
+                        for (int n = 0; n < NT; n++) b[n] = brow[8 * n];
+#pragma unroll
+                        for (int n = 0; n < NT; n++) {
+                            dmma(acc[0][n][0], acc[0][n][1], xv[0][ks], b[n]);
+                            dmma(acc[1][n][0], acc[1][n][1], xv[1][ks], b[n]);
+                        }
                     }
-                }
-            }
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                if (p0 + q < M) {
-                    const size_t o = roff(p0 + q);
-                    const double gpa = s.G[o + xa], gpb = s.G[o + xb];
-                    quad_a = fma(za[q], gpa, quad_a); quad_b = fma(zb[q], gpb, quad_b);
-                    if (v) { lin_a = fma(gpa, v[p0 + q], lin_a); lin_b = fma(gpb, v[p0 + q], lin_b); }
+                    for (int ks = 0; ks < 4; ks++) { xv[0][ks] = xn[0][ks]; xv[1][ks] = xn[1][ks]; xn[0][ks] = xn2[0][ks]; xn[1][ks] = xn2[1][ks]; }
                 }
             }
         }
-        if (la) emit(ca, quad_a, lin_a);
-        if (lb) emit(cb, quad_b, lin_b);
+        if (!resident) { __pipeline_wait_prior(0); __syncthreads(); }
+    }
+    if (live) {
+#pragma unroll
+        for (int n = 0; n < NT; n++)
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int pp = p0 + 8 * n + 2 * gk + i;
+                if (pp < M) {
+                    const size_t o = roff(pp);
+                    const double g0 = G[o + c0], g1 = G[o + c1];
+                    q[0] = fma(acc[0][n][i], g0, q[0]);
+                    q[1] = fma(acc[1][n][i], g1, q[1]);
+                    if (v) { const double vp = v[pp]; l[0] = fma(g0, vp, l[0]); l[1] = fma(g1, vp, l[1]); }
+                }
+            }
+    }
+}
+
+template <class Emit>
+__device__ inline void quad_forms(const Slab &s, const double *sigma, double *sigp_global, int M, int Kc, const double *v,
+                                  double *smem /* >= 2*KT*LDS_V + 784 doubles */, Emit emit)
+{
+    PHASE(PH_QUAD);
+    const int T = blockDim.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    const int gm = lane >> 2, gk = lane & 3;
+    const int ldp = (M + 7) & ~7, Mp = ((M + KT - 1) / KT) * KT;
+    const bool resident = Mp <= 2 * KT;
+    size_t *rowoff = M <= 784 ? reinterpret_cast<size_t *>(smem + 2 * KT * LDS_V) : nullptr;
+    __syncthreads();
+    // zero-padded copy sigp[j][p] = SIGMA(p, j): straight into the shared tile layout when resident
+    if (resident) {
+        for (int idx = threadIdx.x; idx < Mp * ldp; idx += T) {
+            const int j = idx / ldp, p = idx - j * ldp;
+            smem[j * LDS_V + p] = (j < M && p < M) ? sigma[p * M + j] : 0.0;
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < Mp * ldp; idx += T) {
+            const int j = idx / ldp, p = idx - j * ldp;
+            sigp_global[idx] = (j < M && p < M) ? sigma[p * M + j] : 0.0;
+        }
+    }
+    if (rowoff) for (int j = threadIdx.x; j < M; j += T) rowoff[j] = (size_t)s.grow[j] * Kc;
+    __syncthreads();
+    const int n_mtile = (Kc + 7) >> 3;
+    const int per_round = nw * MT;
+    const int nround = (n_mtile + per_round - 1) / per_round;
+    for (int rd = 0; rd < nround; rd++) {
+        const int mt0 = rd * per_round + wid;
+        const bool live = mt0 < n_mtile;
+        const int ca = mt0 * 8 + gm, cb = (mt0 + nw) * 8 + gm;
+        const int c0 = min(ca, Kc - 1), c1 = min(cb, Kc - 1);
+        double q[MT] = {0.0, 0.0}, l[MT] = {0.0, 0.0};
+        for (int p0 = 0; p0 < ldp; p0 += 8 * NT_MAX) {
+            const int nt = min(NT_MAX, (ldp - p0) >> 3);
+            switch (nt) {
+            case 1: quad_chunk<1>(s.G, rowoff, s.grow, M, Kc, sigp_global, ldp, p0, smem, resident, live, c0, c1, v, q, l); break;
+            case 2: quad_chunk<2>(s.G, rowoff, s.grow, M, Kc, sigp_global, ldp, p0, smem, resident, live, c0, c1, v, q, l); break;
+            case 3: quad_chunk<3>(s.G, rowoff, s.grow, M, Kc, sigp_global, ldp, p0, smem, resident, live, c0, c1, v, q, l); break;
+            default: quad_chunk<4>(s.G, rowoff, s.grow, M, Kc, sigp_global, ldp, p0, smem, resident, live, c0, c1, v, q, l); break;
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int t = 0; t < MT; t++) {
+                q[t] += __shfl_xor_sync(0xffffffffu, q[t], 1); q[t] += __shfl_xor_sync(0xffffffffu, q[t], 2);
+                l[t] += __shfl_xor_sync(0xffffffffu, l[t], 1); l[t] += __shfl_xor_sync(0xffffffffu, l[t], 2);
+            }
+            if (gk == 0) {
+                if (ca < Kc) emit(ca, q[0], l[0]);
+                if (cb < Kc) emit(cb, q[1], l[1]);
+            }
+        }
     }
     __syncthreads();
 }
@@ -213,10 +515,11 @@ __device__ inline void quad_forms(const Slab &s, const double *sigma, double *si
 // dot products of active columns with a vector: out[i] = sum_h phi_i[h] * v[h], one warp per i.
 __device__ inline void phi_dot(const double *phi, int N, int M, const double *v, double *out, double scale)
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5, LD = phi_ld(N);
     for (int i = wid; i < M; i += nw) {
-        const double *p = phi + (size_t)i * N;
+        const double *p = phi + (size_t)i * LD;
         double z = 0;
+#pragma unroll 8
         for (int h = lane; h < N; h += 32) z = fma(p[h], v[h], z);
         z = warp_sum(z);
         if (lane == 0) out[i] = z * scale;
@@ -339,175 +642,99 @@ __device__ inline bool spd_inverse_sweep(double *a, int M, double *colk, const S
     return ok;
 }
 
-// Gram matrix of the active columns, H(j, k) = sum_h (phi_j[h] * w[h]) * phi_k[h]  for j <= k (mirrored),
+// Gram matrix of the active columns, H(j, k) = sum_h (phi_j[h] * w[h]) * phi_k[h]  for j <= k,
 // w = nullptr meaning all ones.  This is FinalUpdate*'s PHI'PHI (MainEff.c:1869-1874) and the IRLS
 // Hessian PHI'B PHI (NEmainEff.c:1911-1919, same (phi_j * beta) * phi_k order for the upper triangle
-// the Cholesky reads).  64 x 64 panels; per panel the block streams 32-row tiles of the two column
-// groups through shared memory and every thread accumulates a 4 x 4 register block over all rows
-// in ascending h -- 16 FMAs per four 16-byte shared loads, no shuffles.
-//   smem: 2 * GR_ROWS * GR_LD doubles.   out(j, k, value) is called once per j <= k.
-constexpr int GR_ROWS = 32, GR_COLS = 64, GR_LD = GR_COLS + 2;
-constexpr int GRAM_DOUBLES = 2 * GR_ROWS * GR_LD;
+// the Cholesky reads).  Tensor-core form with no shared-memory staging and no barrier in the main loop:
+// the upper triangle is cut into 16 x 16 blocks (2 x 2 DMMA tiles); a work item is one block over one
+// contiguous range of rows; warps take items round-robin and read their A/B fragments (4 rows x 8 columns,
+// one element per lane) straight from the column-major PHI, one k-step ahead of the DMMAs.  With few
+// blocks (small M) the rows are split so that every warp has work, and the per-split partial tiles are
+// combined through shared memory in a fixed order.
+//   sm: GRAM_DOUBLES doubles.   out(j, k, value) is called exactly once per j <= k.
+constexpr int GRAM_DOUBLES = 5120;
 
 template <class Out>
-__device__ inline void gram_tiled(const double *__restrict__ phi, int N, int M, const double *__restrict__ w,
-                                  double *sm, Out out)
+__device__ inline void gram_mma(const double *__restrict__ phi, int N, int LD, int M, const double *__restrict__ w,
+                                double *sm, Out out)
 {
     PHASE(PH_GRAM);
-    double *sA = sm, *sB = sm + GR_ROWS * GR_LD;
-    const int T = blockDim.x;
-    const int npan = (M + GR_COLS - 1) / GR_COLS, ntile = (N + GR_ROWS - 1) / GR_ROWS;
-    for (int pj = 0; pj < npan; pj++)
-        for (int pk = pj; pk < npan; pk++) {
-            const int j0 = pj * GR_COLS, k0 = pk * GR_COLS;
-            const int nbj = (min(GR_COLS, M - j0) + 3) >> 2, nbk = (min(GR_COLS, M - k0) + 3) >> 2;
-            // 4 x 4 register blocks needed in this panel: all of them off the diagonal, the upper triangle on it.
-            const int nblk = pj == pk ? nbj * (nbj + 1) / 2 : nbj * nbk;
-            // Threads left over are used to split the rows: block b is accumulated by `nsplit` threads,
-            // thread (b, s) taking row tiles s, s + nsplit, ...; partial sums are combined in fixed order.
-            const int nsplit = max(1, min(min(T, 256) / nblk, ntile));
-            const int blk = threadIdx.x % nblk, split = threadIdx.x / nblk;
-            const bool active = threadIdx.x < nblk * nsplit;
-            int bj = 0, bk = blk;
-            if (pj == pk) { int rem = blk; while (rem >= nbj - bj) { rem -= nbj - bj; bj++; } bk = bj + rem; }
-            else { bj = blk / nbk; bk = blk - bj * nbk; }
-            double acc[4][4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int gm = lane >> 2, gk = lane & 3;
+    const int nt = (M + 7) >> 3, ntb = (nt + 1) >> 1, P = ntb * (ntb + 1) / 2;
+    const int ng = (N + 15) >> 4;                              // groups of 16 rows; lane gk owns rows 4*gk .. 4*gk+3 of a group
+    int RS = 1;
+    if (P < 2 * nw) RS = max(1, min(min((2 * nw + P - 1) / P, GRAM_DOUBLES / (256 * P)), ng / 2));
+    const int items = P * RS, gsplit = (ng + RS - 1) / RS;
+    __syncthreads();
+    for (int item = wid; item < items; item += nw) {
+        const int pb = item % P, sp = item / P;
+        int Jb = 0, Kb = pb;
+        { int rem = pb; while (rem >= ntb - Jb) { rem -= ntb - Jb; Jb++; } Kb = Jb + rem; }
+        const bool diag = Jb == Kb;
+        const int g0 = sp * gsplit, g1 = min(ng, g0 + gsplit);
+        const double *pa0 = phi + (size_t)min(16 * Jb + gm, M - 1) * LD, *pa1 = phi + (size_t)min(16 * Jb + 8 + gm, M - 1) * LD;
+        const double *pb0 = phi + (size_t)min(16 * Kb + gm, M - 1) * LD, *pb1 = phi + (size_t)min(16 * Kb + 8 + gm, M - 1) * LD;
+        double acc[2][2][2];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+        for (int a = 0; a < 2; a++)
 #pragma unroll
-                for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-            for (int ti = 0; ti < ntile; ti++) {
-                const int h0 = ti * GR_ROWS;
-                __syncthreads();
-                for (int idx = threadIdx.x; idx < GR_ROWS * GR_COLS; idx += T) {
-                    const int hl = idx & (GR_ROWS - 1), cl = idx >> 5;         // consecutive threads -> consecutive rows
-                    const int h = h0 + hl;
-                    double va = 0.0, vb = 0.0;
-                    if (h < N) {
-                        if (j0 + cl < M) { va = phi[(size_t)(j0 + cl) * N + h]; if (w) va *= w[h]; }
-                        if (k0 + cl < M) vb = phi[(size_t)(k0 + cl) * N + h];
-                    }
-                    sA[hl * GR_LD + cl] = va; sB[hl * GR_LD + cl] = vb;
-                }
-                __syncthreads();
-                if (active && ti % nsplit == split) {
-#pragma unroll 4
-                    for (int hl = 0; hl < GR_ROWS; hl++) {
-                        const double2 *pa = reinterpret_cast<const double2 *>(sA + hl * GR_LD + 4 * bj);
-                        const double2 *pb = reinterpret_cast<const double2 *>(sB + hl * GR_LD + 4 * bk);
-                        const double2 a01 = pa[0], a23 = pa[1], b01 = pb[0], b23 = pb[1];
-                        const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                        for (int a = 0; a < 4; a++)
-#pragma unroll
-                            for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-                    }
-                }
+            for (int b = 0; b < 2; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+        struct Frag { double a0[4], a1[4], b0[4], b1[4], ww[4]; };
+        auto fetch = [&](int g, Frag &f) {
+            const int h = 16 * g + 4 * gk, hc = min(h, LD - 4);     // whole quads past the padded column are clamped (weight 0)
+            const double2 *q;
+            q = reinterpret_cast<const double2 *>(pa0 + hc); { const double2 u = q[0], v2 = q[1]; f.a0[0] = u.x; f.a0[1] = u.y; f.a0[2] = v2.x; f.a0[3] = v2.y; }
+            q = reinterpret_cast<const double2 *>(pa1 + hc); { const double2 u = q[0], v2 = q[1]; f.a1[0] = u.x; f.a1[1] = u.y; f.a1[2] = v2.x; f.a1[3] = v2.y; }
+            if (!diag) {
+                q = reinterpret_cast<const double2 *>(pb0 + hc); { const double2 u = q[0], v2 = q[1]; f.b0[0] = u.x; f.b0[1] = u.y; f.b0[2] = v2.x; f.b0[3] = v2.y; }
+                q = reinterpret_cast<const double2 *>(pb1 + hc); { const double2 u = q[0], v2 = q[1]; f.b1[0] = u.x; f.b1[1] = u.y; f.b1[2] = v2.x; f.b1[3] = v2.y; }
             }
-            __syncthreads();                       // tiles are dead: reuse the buffer for the partial sums
-            if (active) {
-                double *dst = sm + ((size_t)split * nblk + blk) * 16;
 #pragma unroll
-                for (int a = 0; a < 4; a++)
+            for (int i = 0; i < 4; i++) f.ww[i] = (h + i < N) ? (w ? w[h + i] : 1.0) : 0.0;      // rows past N contribute nothing
+        };
+        Frag cur, nxt;
+        if (g0 < g1) fetch(g0, cur);
+        for (int g = g0; g < g1; g++) {
+            fetch(min(g + 1, g1 - 1), nxt);
 #pragma unroll
-                    for (int b = 0; b < 4; b++) dst[a * 4 + b] = acc[a][b];
+            for (int ks = 0; ks < 4; ks++) {
+                const double wa0 = cur.a0[ks] * cur.ww[ks], wa1 = cur.a1[ks] * cur.ww[ks];
+                const double b0 = diag ? cur.a0[ks] : cur.b0[ks], b1 = diag ? cur.a1[ks] : cur.b1[ks];
+                dmma(acc[0][0][0], acc[0][0][1], wa0, b0);
+                dmma(acc[0][1][0], acc[0][1][1], wa0, b1);
+                if (!diag) dmma(acc[1][0][0], acc[1][0][1], wa1, b0);  // below the diagonal inside a diagonal block: not needed
+                dmma(acc[1][1][0], acc[1][1][1], wa1, b1);
             }
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < nblk * 16; idx += T) {
-                const int b2 = idx >> 4, e = idx & 15, a = e >> 2, b = e & 3;
+            cur = nxt;
+        }
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    if (RS == 1) {
+                        const int j = 16 * Jb + 8 * a + gm, k = 16 * Kb + 8 * b + 2 * gk + i;
+                        if (j < M && k < M && j <= k) out(j, k, acc[a][b][i]);
+                    } else {
+                        sm[(size_t)item * 256 + (a * 2 + b) * 64 + gm * 8 + 2 * gk + i] = acc[a][b][i];
+                    }
+                }
+    }
+    if (RS > 1) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < P * 256; idx += blockDim.x) {
+            const int pb = idx >> 8, e = idx & 255, tile = e >> 6, a = tile >> 1, b = tile & 1, m = (e >> 3) & 7, n = e & 7;
+            int Jb = 0, Kb = pb;
+            { int rem = pb; while (rem >= ntb - Jb) { rem -= ntb - Jb; Jb++; } Kb = Jb + rem; }
+            const int j = 16 * Jb + 8 * a + m, k = 16 * Kb + 8 * b + n;
+            if (j < M && k < M && j <= k) {
                 double z = 0.0;
-                for (int sp = 0; sp < nsplit; sp++) z += sm[((size_t)sp * nblk + b2) * 16 + e];
-                int cj = 0, ck = b2;
-                if (pj == pk) { int rem = b2; while (rem >= nbj - cj) { rem -= nbj - cj; cj++; } ck = cj + rem; }
-                else { cj = b2 / nbk; ck = b2 - cj * nbk; }
-                const int j = j0 + 4 * cj + a, k = k0 + 4 * ck + b;
-                if (j < M && k < M && j <= k) out(j, k, z);
+                for (int sp = 0; sp < RS; sp++) z += sm[(size_t)(sp * P + pb) * 256 + e];
+                out(j, k, z);
             }
         }
-    __syncthreads();
-}
-
-// Pipelined Gram matrix for at most 64 active columns, from the ROW-major copy PHIt (leading dimension
-// PHIT_LD = 64):  H(j, k) = sum_h (phit[h][j] * w[h]) * phit[h][k],  j <= k.
-// Tiles of 32 rows (16 KB) are streamed with cp.async, double-buffered, so the copy of tile t+1
-// overlaps the FMAs of tile t and there is one barrier per tile (gram_tiled pays two barriers and
-// an exposed global load per tile).  Register blocks, row splitting and the fixed-order combination
-// of partial sums are as in gram_tiled.   smem: 2 * 32 * 64 + 64 doubles (w tiles).
-constexpr int GP_ROWS = 32;
-constexpr int GRAM_PIPE_DOUBLES = 2 * GP_ROWS * PHIT_LD + 2 * GP_ROWS;
-
-template <class Out>
-__device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, const double *__restrict__ w,
-                                 double *sm, Out out)
-{
-    PHASE(PH_GRAM);
-    const int T = blockDim.x;
-    double *tiles = sm, *wt = sm + 2 * GP_ROWS * PHIT_LD;
-    const int ntile = (N + GP_ROWS - 1) / GP_ROWS;
-    const int nb = (M + 3) >> 2, nblk = nb * (nb + 1) / 2;
-    const int nsplit = max(1, min(min(T, 256) / nblk, 8));
-    const int blk = threadIdx.x % nblk, split = threadIdx.x / nblk;
-    const bool active = threadIdx.x < nblk * nsplit;
-    int bj = 0, bk = blk;
-    { int rem = blk; while (rem >= nb - bj) { rem -= nb - bj; bj++; } bk = bj + rem; }
-    const int rps = (GP_ROWS + nsplit - 1) / nsplit;            // rows of a tile per split
-    auto stage = [&](int t) {
-        if (t < ntile) {
-            double *dst = tiles + (t & 1) * (GP_ROWS * PHIT_LD);
-            const int h0 = t * GP_ROWS;
-            for (int idx = threadIdx.x; idx < GP_ROWS * (PHIT_LD / 2); idx += T) {
-                const int hl = idx >> 5, q = idx & 31;          // 32 16-byte pieces per row
-                __pipeline_memcpy_async(dst + hl * PHIT_LD + 2 * q, phit + (size_t)min(h0 + hl, N - 1) * PHIT_LD + 2 * q, 16);
-            }
-            if (threadIdx.x < GP_ROWS) wt[(t & 1) * GP_ROWS + threadIdx.x] = (h0 + (int)threadIdx.x < N) ? (w ? w[h0 + threadIdx.x] : 1.0) : 0.0;
-        }
-        __pipeline_commit();
-    };
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-    __syncthreads();
-    stage(0);
-    for (int t = 0; t < ntile; t++) {
-        __pipeline_wait_prior(0);
-        __syncthreads();                                         // tile t visible; everyone finished tile t-1
-        stage(t + 1);
-        if (active) {
-            const double *tile = tiles + (t & 1) * (GP_ROWS * PHIT_LD), *wv = wt + (t & 1) * GP_ROWS;
-            const int hb = split * rps, he = min(hb + rps, GP_ROWS);
-#pragma unroll 2
-            for (int hl = hb; hl < he; hl++) {
-                const double4 a4 = *reinterpret_cast<const double4 *>(tile + hl * PHIT_LD + 4 * bj);
-                const double4 b4 = *reinterpret_cast<const double4 *>(tile + hl * PHIT_LD + 4 * bk);
-                const double ww = wv[hl];                        // rows past N carry weight 0
-                const double av[4] = {a4.x * ww, a4.y * ww, a4.z * ww, a4.w * ww}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-            }
-        }
-    }
-    __pipeline_wait_prior(0);
-    __syncthreads();                                             // tiles are dead: reuse the buffer for the partial sums
-    if (active) {
-        double *dst = sm + ((size_t)split * nblk + blk) * 16;
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) dst[a * 4 + b] = acc[a][b];
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nblk * 16; idx += T) {
-        const int b2 = idx >> 4, e = idx & 15, a = e >> 2, b = e & 3;
-        double z = 0.0;
-        for (int sp = 0; sp < nsplit; sp++) z += sm[((size_t)sp * nblk + b2) * 16 + e];
-        int cj = 0, ck = b2;
-        { int rem = b2; while (rem >= nb - cj) { rem -= nb - cj; cj++; } ck = cj + rem; }
-        const int j = 4 * cj + a, k = 4 * ck + b;
-        if (j < M && k < M && j <= k) out(j, k, z);
     }
     __syncthreads();
 }
@@ -576,7 +803,7 @@ __device__ inline bool final_update(Slab &s, GaussState &g, int N, const Scratch
 {   // FinalUpdate*: H = beta PHI'PHI + diag(alpha), SIGMA = H^-1, Mu  (MainEff.c:1841-1921)
     const int M = g.M;
     const double beta = g.beta;
-    gram_tiled(s.phi, N, M, nullptr, sc.sweep, [&](int i, int j, double z) {
+    gram_mma(s.phi, N, phi_ld(N), M, nullptr, sc.sweep, [&](int i, int j, double z) {
         double v = z * beta;
         if (i == j) v += s.alpha[i];
         s.H[j * M + i] = v; s.H[i * M + j] = v;
@@ -674,7 +901,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                           double alpha_en, const FitTask &task, const FitOutputs &out, double *sV,
                           const Scratch &sc)
 {
-    const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x;
+    const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x, LD = phi_ld(N);
     const double *X = F.Xtr, *y = F.ytr, *scale = F.scale;
     GaussState g; g.M = 1; g.n_unused = 0; g.beta = 0; g.status = 0; g.flops = 0;
 
@@ -699,7 +926,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
             g.M = 1;
             if (threadIdx.x == 0) s.used[0] = 1;
             const double isc = 1 / scale[0];
-            for (int h = threadIdx.x; h < N; h += T) s.phi[h] = X[(size_t)h * K] * isc;
+            for (int h = threadIdx.x; h < LD; h += T) s.phi[h] = h < N ? X[(size_t)h * K] * isc : 0.0;      // pad rows stay zero
             __syncthreads();
             const double var = block_var(s.t, N, sc);
             if (!EPIS) g.beta = 1 / (var * 0.01 + 1e-10);
@@ -725,12 +952,10 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
         // candidate cache G = PHI'X/s and xt = X't/s  (CacheBP*, :1144-1201)
         {
             const int M = g.M;
-            contract_x<EPIS>(F, K, Kc, M + 1,
-                [&](int r, int h) { return r < M ? s.phi[(size_t)r * N + h] : s.t[h]; },
-                [&](int r, int c, double acc) {
-                    if (r < M) s.G[(size_t)s.grow[r] * Kc + c] = acc / scale[c];
-                    else s.xt[c] = acc / scale[c];
-                }, s.vbuf, (int)vld(cap), sV);
+            contract_x<EPIS>(F, K, Kc, M + 1, M,
+                [&](int r) -> const double * { return r < M ? s.phi + (size_t)r * LD : s.t; },
+                [&](int r, bool &dv) -> double * { dv = true; return r < M ? s.G + (size_t)s.grow[r] * Kc : s.xt; },
+                sV);
             if (threadIdx.x == 0) g.flops += 2.0 * N * (double)Kc * (M + 1);
         }
         int i_iter = 0;
@@ -778,6 +1003,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                         selected = ACT_TERM;                                       // :541-549
                     const int M = g.M;
                     bool updated = false;
+                    { PHASE(PH_ACTIONS);
                     if (selected == ACT_REEST) {                                   // :553-596
                         const double old = s.alpha[jj];
                         const double kappa = 1.0 / (s.sigma[jj * M + jj] + 1.0 / (new_alpha - old));
@@ -815,16 +1041,16 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             }
                             __syncthreads();
                             const int grow_new = s.grow[M];
-                            contract_x<EPIS>(F, K, Kc, 1,
-                                [&](int, int h) { return s.phinew[h]; },
-                                [&](int, int c, double acc) { s.G[(size_t)grow_new * Kc + c] = acc / scale[c]; }, s.vbuf, (int)vld(cap), sV);
+                            contract_x<EPIS>(F, K, Kc, 1, 0,
+                                [&](int) -> const double * { return s.phinew; },
+                                [&](int, bool &dv) -> double * { dv = true; return s.G + (size_t)grow_new * Kc; }, sV);
                             phi_dot(s.phi, N, M, s.phinew, s.tmp, g.beta);             // tmp = beta PHI' phi
                             for (int i = threadIdx.x; i < M; i += T) {
                                 double z = 0;
                                 for (int j = 0; j < M; j++) z = fma(s.sigma[i * M + j], s.tmp[j], z);
                                 s.u[i] = z;
                             }
-                            for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)M * N + h] = s.phinew[h];
+                            for (int h = threadIdx.x; h < LD; h += T) s.phi[(size_t)M * LD + h] = h < N ? s.phinew[h] : 0.0;
                             const double s_ii = 1.0 / (new_alpha + s.S_in[nu]);
                             const double mu_i = s_ii * s.Q_in[nu];
                             __syncthreads();
@@ -871,7 +1097,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             double m = s.mu[i] - mujj * sj[i] / sjj;
                             s.mu[i] = m;
                         }
-                        for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)jj * N + h] = s.phi[(size_t)lastj * N + h];
+                        for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)jj * LD + h] = s.phi[(size_t)lastj * LD + h];
                         // Schur downdate, then move the last row/column into slot jj (:1754-1776)
                         for (int idx = threadIdx.x; idx < lastj * lastj; idx += T) {
                             const int j = idx / lastj, i = idx - j * lastj;
@@ -904,7 +1130,9 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                         updated = true;
                     }
                     __syncthreads();
+                    }
                     if (updated) {                                                 // :657-681
+                        PHASE(PH_OTHER);
                         double *tmpp = s.sigma; s.sigma = s.sigma_new; s.sigma_new = tmpp;
                         refresh_out(s, g.M, Kc);
                         const int Mn = g.M;
@@ -916,13 +1144,16 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
             if (selected == ACT_TERM || i_iter <= 10 || i_iter % 5 == 0 || n_update >= 2) {      // :685-729
                 const int M = g.M;
                 double ee = 0;
+                { PHASE(PH_LOGLIK);
                 for (int h = threadIdx.x; h < N; h += T) {
                     double pm = 0;
-                    for (int j = 0; j < M; j++) pm = fma(s.phi[(size_t)j * N + h], s.mu[j], pm);
+#pragma unroll 8
+                    for (int j = 0; j < M; j++) pm = fma(s.phi[(size_t)j * LD + h], s.mu[j], pm);
                     const double e = s.t[h] - pm;
                     ee = fma(e, e, ee);
                 }
                 ee = block_sum(ee, sc);
+                }
                 double sg = 0;
                 for (int i = 0; i < M; i++) sg += s.gamma[i];
                 const double beta_old = g.beta;
@@ -943,7 +1174,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
             const int M = g.M;
             const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
             for (int j = wid; j < M; j += nw) {
-                const double *p = s.phi + (size_t)j * N;
+                const double *p = s.phi + (size_t)j * LD;
                 double a1 = 0, ay = 0;
                 for (int h = lane; h < N; h += 32) { a1 += p[h]; ay = fma(p[h], y[h], ay); }
                 a1 = warp_sum(a1); ay = warp_sum(ay);

@@ -5,8 +5,7 @@
 //  the hot loops use explicit fma()).
 #include "../../include/pareben.h"
 #include "common.cuh"
-#include "gauss_fit.cuh"
-#include "binom_fit.cuh"
+#include "fit_launch.h"
 
 #include <algorithm>
 #include <chrono>
@@ -105,6 +104,25 @@ __global__ void to_int8_kernel(const double *__restrict__ in, size_t n, int8_t *
         out[i] = (int8_t)in[i];
 }
 
+// Transposed, row-padded copy of a row-major matrix: out[k*ldt + r] = X[r*K + k] (zero for r >= nrows), as int8 or f64.
+template <class T>
+__global__ void transpose_pad_kernel(const double *__restrict__ X, int nrows, int K, int ldt, T *__restrict__ out)
+{
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int r = r0 + rr, k = k0 + threadIdx.x;
+        tile[rr][threadIdx.x] = (r < nrows && k < K) ? X[(size_t)r * K + k] : 0.0;
+    }
+    __syncthreads();
+    for (int kk = threadIdx.y; kk < 32; kk += blockDim.y) {
+        const int r = r0 + threadIdx.x, k = k0 + kk;
+        // rows of every group of 16 are stored permuted: physical position 4a + b holds row 4b + a (see mma_pass)
+        const int rp = (r & ~15) | ((r & 3) << 2) | ((r >> 2) & 3);
+        if (r < ldt && k < K) out[(size_t)k * ldt + rp] = (T)tile[threadIdx.x][kk];
+    }
+}
+
 // scale[c] = sqrt(sum_h x_c[h]^2), 1 when the column is all zero (MainEff.c:87-99, NeFull2.c:100-135)
 template <bool EPIS>
 __global__ void scales_kernel(const double *__restrict__ X, int N, int K, int Kc, double *__restrict__ scale)
@@ -139,42 +157,6 @@ __global__ void lambda_max_kernel(const double *__restrict__ X, int N, int K, in
         double m = red[0];
         for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmax(m, red[w]);
         block_max[blockIdx.x] = m;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// the persistent batched-fit kernel: one block = one fit at a time, fits pulled from a queue
-constexpr int FIT_THREADS = 256;     // compile-time maximum (register budget: 2 x 256 or 4 x 128 threads per SM)
-
-template <bool EPIS, bool BINOMIAL>
-__global__ void __launch_bounds__(FIT_THREADS, 2)
-eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_tasks, int *queue, char *slabs,
-                size_t slab_stride, FitOutputs out)
-{
-    // One shared buffer, used by phases that never overlap: the double-buffered right-hand-side tiles of
-    // the contraction (first SV_DOUBLES doubles) and the in-shared-memory sweep of small inverses.
-    constexpr int SWEEP_DOUBLES = SWEEP_SMEM_M * SWEEP_SMEM_M + 2 * SWEEP_SMEM_M;
-    constexpr int BUF_A = SWEEP_DOUBLES > SV_DOUBLES ? SWEEP_DOUBLES : SV_DOUBLES;
-    constexpr int BUF_B = BUF_A > GRAM_DOUBLES ? BUF_A : GRAM_DOUBLES;
-    constexpr int BUF_C = BUF_B > GRAM_PIPE_DOUBLES ? BUF_B : GRAM_PIPE_DOUBLES;
-    constexpr int QUAD_DOUBLES = 4096 + 1040;
-    __shared__ __align__(32) double s_buf[BUF_C > QUAD_DOUBLES ? BUF_C : QUAD_DOUBLES];
-    double *sV = s_buf;
-    __shared__ double red[66];
-    __shared__ int redi[66];
-    __shared__ int s_task;
-    Scratch sc{red, redi, s_buf};
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_task = atomicAdd(queue, 1);
-        __syncthreads();
-        const int ti = s_task;
-        if (ti >= n_tasks) break;
-        const FitTask task = tasks[ti];
-        const FoldData F = P.folds[task.fold];
-        Slab s = carve_slab(slabs + (size_t)blockIdx.x * slab_stride, P.cap, P.nmax, P.Kc);
-        if (BINOMIAL) binom_fit<EPIS>(P, F, v, s, task.lambda, task.alpha, task, out, sV, sc);
-        else gauss_fit<EPIS>(P, F, v, s, task.lambda, task.alpha, task, out, sV, sc);
     }
 }
 
@@ -318,7 +300,7 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         lap("stream/events/h2d enqueue/scan");
         // row lists per fold: index 0 = all rows (only materialised when n_folds == 0)
         const int nf = n_folds;
-        p->h_folds.assign(nf + 1, FoldData{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0});
+        p->h_folds.assign(nf + 1, FoldData{});
         int min_ntr = n;
         for (int f = (nf == 0 ? 0 : 1); f <= nf; f++) {
             std::vector<int> tr, te;
@@ -352,6 +334,20 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
             if (epis) scales_kernel<true><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
             else scales_kernel<false><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
             F.Xtr = Xtr; F.ytr = ytr; F.Xte = Xte; F.yte = yte; F.scale = scale; F.Xtr8 = nullptr;
+            F.XT8 = nullptr; F.XTd = nullptr;
+            F.ldt = (F.ntr + 31) & ~31;
+            {
+                const dim3 tg((F.ldt + 31) / 32, (k + 31) / 32);
+                if (small_int) {
+                    int8_t *t8 = p->dalloc<int8_t>((size_t)F.ldt * k + 16);
+                    transpose_pad_kernel<int8_t><<<tg, blk, 0, p->stream>>>(Xtr, F.ntr, k, F.ldt, t8);
+                    F.XT8 = t8;
+                } else {
+                    double *td = p->dalloc<double>((size_t)F.ldt * k + 4);
+                    transpose_pad_kernel<double><<<tg, blk, 0, p->stream>>>(Xtr, F.ntr, k, F.ldt, td);
+                    F.XTd = td;
+                }
+            }
             if (small_int) {
                 int8_t *x8 = p->dalloc<int8_t>((size_t)F.ntr * k + 16);
                 to_int8_kernel<<<std::min<size_t>(1024, ((size_t)F.ntr * k + 255) / 256), 256, 0, p->stream>>>(Xtr, (size_t)F.ntr * k, x8);
@@ -380,15 +376,13 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         {
             // Block size: measured on B200 (config 2 / bundled Gaussian): 256 threads x 2 blocks per SM beats
             // 128 x 4 (-5 % / -43 %) and 64 x 8 (-40 % / -70 %) (measured with an earlier build that had a run-time block size).
-            p->threads = FIT_THREADS;     // gram_tiled() maps 16 x 16 register blocks onto exactly 256 threads
+            p->threads = FIT_THREADS_HOST;     // gram_tiled() maps 16 x 16 register blocks onto exactly 256 threads
             static int occ_cache[4] = {0, 0, 0, 0};
             int &occ = occ_cache[(prior == PAREBEN_BINOMIAL ? 2 : 0) + (epis ? 1 : 0)];
             if (!occ) {
                 cudaError_t e;
-                if (prior == PAREBEN_GAUSSIAN) e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, false>, p->threads, 0)
-                                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, false>, p->threads, 0);
-                else e = epis ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<true, true>, p->threads, 0)
-                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eben_fit_kernel<false, true>, p->threads, 0);
+                if (prior == PAREBEN_GAUSSIAN) e = epis ? occupancy_ge(&occ, p->threads) : occupancy_gm(&occ, p->threads);
+                else e = epis ? occupancy_be(&occ, p->threads) : occupancy_bm(&occ, p->threads);
                 CU(e);
             }
             per_sm = std::max(1, occ);
@@ -496,14 +490,10 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
         const Variant v = make_variant(p->epis, p->prior);
         const int grid = std::min(p->n_slabs, n_fits);
         CU(cudaEventRecord(p->ev0, p->stream));
-        if (p->prior == PAREBEN_GAUSSIAN) {
-            if (p->epis) eben_fit_kernel<true, false><<<grid, p->threads, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
-            else eben_fit_kernel<false, false><<<grid, p->threads, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
-        } else {
-            if (p->epis) eben_fit_kernel<true, true><<<grid, p->threads, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
-            else eben_fit_kernel<false, true><<<grid, p->threads, 0, p->stream>>>(P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out);
-        }
-        CU(cudaGetLastError());
+        if (p->prior == PAREBEN_GAUSSIAN)
+            CU((p->epis ? launch_fit_ge : launch_fit_gm)(grid, p->threads, p->stream, P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out));
+        else
+            CU((p->epis ? launch_fit_be : launch_fit_bm)(grid, p->threads, p->stream, P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out));
         CU(cudaEventRecord(p->ev1, p->stream));
         std::vector<int> h_ints(3 * (size_t)n_fits);
         std::vector<double> h_err(n_fits);
@@ -706,18 +696,34 @@ extern "C" int pareben_lambda_max(pareben_problem *p, double *lambda_max)
     return PAREBEN_OK;
 }
 
-// experiments only: cycles per phase summed over blocks (zeros unless built with -DPAREBEN_PHASE_TIMING)
+// experiments only (timing build, -DPAREBEN_PHASE_TIMING): cycles per phase summed over blocks and over the
+// four kernel variants; zeros in the normal build.  out: PH_COUNT cycle totals then PH_COUNT call counts.
 extern "C" int pareben_phase_cycles(unsigned long long *out, int reset)
 {
-#ifdef PAREBEN_PHASE_TIMING
-    if (out) { cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * PH_COUNT);
-               cudaMemcpyFromSymbol(out + PH_COUNT, g_phase_calls, sizeof(unsigned long long) * PH_COUNT); }
-    if (reset) { unsigned long long z[PH_COUNT] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z); cudaMemcpyToSymbol(g_phase_calls, z, sizeof z); }
-#else
-    if (out) for (int i = 0; i < 2 * PH_COUNT; i++) out[i] = 0;
-    (void)reset;
-#endif
+    unsigned long long acc[2 * PH_COUNT] = {0}, one[2 * PH_COUNT];
+    void (*fn[4])(unsigned long long *, int, unsigned long long *, unsigned long long *, int *, int) = {timing_gm, timing_ge, timing_bm, timing_be};
+    for (int i = 0; i < 4; i++) {
+        for (int j = 0; j < 2 * PH_COUNT; j++) one[j] = 0;
+        fn[i](one, reset, nullptr, nullptr, nullptr, 0);
+        for (int j = 0; j < 2 * PH_COUNT; j++) acc[j] += one[j];
+    }
+    if (out) for (int j = 0; j < 2 * PH_COUNT; j++) out[j] = acc[j];
     return PH_COUNT;
+}
+
+// experiments only: per-fit start/end (%globaltimer ns) and block id of the last launch of variant
+// `which` (0 gm, 1 ge, 2 bm, 3 be); returns 0 in the normal build.
+extern "C" int pareben_fit_trace(int which, unsigned long long *t0, unsigned long long *t1, int *block, int n)
+{
+#ifdef PAREBEN_PHASE_TIMING
+    void (*fn[4])(unsigned long long *, int, unsigned long long *, unsigned long long *, int *, int) = {timing_gm, timing_ge, timing_bm, timing_be};
+    if (which < 0 || which > 3) return 0;
+    fn[which](nullptr, 0, t0, t1, block, n);
+    return n;
+#else
+    (void)which; (void)t0; (void)t1; (void)block; (void)n;
+    return 0;
+#endif
 }
 
 extern "C" int pareben_last_counters(pareben_problem *p, double *flops, double *kernel_ms, int *launches)
