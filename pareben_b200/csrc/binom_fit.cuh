@@ -36,7 +36,6 @@ __device__ inline double predictor_and_error(const Slab &s, int N, int M, const 
     const int LD = phi_ld(N);
     for (int h = threadIdx.x; h < N; h += blockDim.x) {
         double z = 0;
-#pragma unroll 8
         for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * LD + h], mu[j], z);
         eta[h] = z;
         const double y = 1 / (1 + exp(-z));
@@ -83,7 +82,6 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
         for (int j = 1 + wid; j < M; j += nw) {
             const double *ph = s.phi + (size_t)j * LD;
             double gj = 0;
-#pragma unroll 8
             for (int h = lane; h < N; h += 32) gj = fma(ph[h], e[h], gj);
             gj = warp_sum(gj);
             if (lane == 0) g[j] = gj - s.alpha[j - 1] * s.mu[j];
@@ -92,7 +90,8 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
             if (j == k && j > 0) z += s.alpha[k - 1];
             s.H[k * M + j] = z; s.H[j * M + k] = z;
         };
-        gram_mma(s.phi, N, LD, M, w, sc.sweep, put);
+        if (M <= PHIT_LD && blockDim.x == 256) gram_pipe(s.phit, N, M, w, sc.sweep, put);   // row-major copy, pipelined
+        else gram_mma(s.phi, N, LD, M, w, sc.sweep, put);
         for (int idx = threadIdx.x; idx < M * M; idx += T) s.sigma[idx] = s.H[idx];
         __syncthreads();
         if (!spd_inverse_sweep(s.sigma, M, s.colk, sc, sc.sweep)) b.status |= ST_NOT_PD;
@@ -136,7 +135,6 @@ __device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab
     double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2;
     for (int h = threadIdx.x; h < N; h += T) {
         double z = 0;
-#pragma unroll 8
         for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * LD + h], s.mu[j], z);
         eta[h] = z;
         const double y = 1 / (1 + exp(-z));
@@ -188,6 +186,9 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                 const double x = X[(size_t)h * K];
                 const double p1 = EPIS ? x / sc0 : x * isc;                   // NeFull.c:93 vs NEmainEff.c:1347-1350
                 s.phi[(size_t)LD + h] = p1;
+                double *pr = s.phit + (size_t)h * PHIT_LD;                    // row-major copy for the IRLS Gram matrix
+                pr[0] = 1; pr[1] = p1;
+                for (int j = 2; j < PHIT_LD; j++) pr[j] = 0;
             }
             __syncthreads();
             // least squares of [1 phi] on the pseudo-logits (dgelsy with rcond 1e-5, :1366-1370):
@@ -317,7 +318,6 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                                 for (int i = wid; i < M; i += nw) {
                                     const double *p = s.phi + (size_t)i * LD;
                                     double z = 0;
-#pragma unroll 8
                                     for (int h = lane; h < N; h += 32) z = fma(p[h], s.w1[h] * s.phinew[h], z);
                                     z = warp_sum(z);
                                     if (lane == 0) s.tmp[i] = z;
@@ -332,6 +332,7 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                             for (int h = N + threadIdx.x; h < LD; h += T) s.phi[(size_t)M * LD + h] = 0;
                             for (int h = threadIdx.x; h < N; h += T) {
                                 s.phi[(size_t)M * LD + h] = s.phinew[h];
+                                if (M < PHIT_LD) s.phit[(size_t)h * PHIT_LD + M] = s.phinew[h];
                             }
                             const double s_ii = 1.0 / (new_alpha + s.S_in[nu]);
                             const double mu_i = s_ii * s.Q_in[nu];
@@ -393,8 +394,11 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                         }
                         for (int h = threadIdx.x; h < N; h += T) {
                             if (j1 != lastj) {
-                                s.phi[(size_t)j1 * LD + h] = s.phi[(size_t)lastj * LD + h];
+                                const double pv = s.phi[(size_t)lastj * LD + h];
+                                s.phi[(size_t)j1 * LD + h] = pv;
+                                if (j1 < PHIT_LD) s.phit[(size_t)h * PHIT_LD + j1] = pv;
                             }
+                            if (lastj < PHIT_LD) s.phit[(size_t)h * PHIT_LD + lastj] = 0;     // vacated slot back to zero
                         }
                         __syncthreads();
                         if (threadIdx.x == 0) {
@@ -428,7 +432,6 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                 double ll = 0;
                 for (int h = threadIdx.x; h < N; h += T) {
                     double z = 0;
-#pragma unroll 8
                     for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * LD + h], s.mu[j], z);
                     const double ez = exp(z);
                     ll += t[h] * log(ez / (1 + ez)) + (1 - t[h]) * log(1 / (1 + ez));

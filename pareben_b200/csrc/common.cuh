@@ -38,7 +38,7 @@ struct FoldData {
     const double *yte;       // [nte]
     const double *scale;     // [Kc] column norms of the training rows (1 where the column is all zero)
     // column-major (transposed) copies for the tensor-core contraction: column k at XT + k*ldt, rows zero-padded
-    // to ldt (a multiple of 32).  Exactly one of the two is non-null (int8 when Xtr8 is).
+    // to ldt (a multiple of 64).  Exactly one of the two is non-null (int8 when Xtr8 is).
     const int8_t *XT8;
     const double *XTd;
     int ldt;
@@ -66,6 +66,7 @@ struct FitOutputs {
 struct Slab {
     double *sigma, *sigma_new, *H;      // cap*cap each
     double *phi;                        // phi_ld(nmax) * cap, column-major (column j at phi + j*phi_ld(N), pad rows zero)
+    double *phit;                       // (nmax + 32) * PHIT_LD: row-major copy of the first PHIT_LD active columns (binomial IRLS)
     double *G;                          // cap * Kc: physical rows, row r at G + r*Kc
     double *xt, *S_in, *Q_in, *S_out, *Q_out, *dml, *aroot;   // Kc each
     double *t, *e, *phinew, *w1, *w2;   // nmax each
@@ -82,10 +83,11 @@ __host__ __device__ inline size_t sig_elems(int cap) { return (((size_t)(cap + 3
 // leading dimension of the column-major active-column matrix PHI: rows padded to a multiple of 4 so that a lane
 // can fetch four consecutive rows of a column with 16-byte loads (the pad rows are kept at zero)
 __host__ __device__ inline int phi_ld(int n) { return (n + 3) & ~3; }
+constexpr int PHIT_LD = 64;       // row-major copy of the first 64 active columns (binomial IRLS Gram matrix)
 
 __host__ __device__ inline size_t slab_doubles(int cap, int nmax, int Kc)
 {
-    return 3 * sig_elems(cap) + (size_t)phi_ld(nmax) * cap + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
+    return 3 * sig_elems(cap) + (size_t)phi_ld(nmax) * cap + (size_t)(nmax + 32) * PHIT_LD + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
            (size_t)7 * (cap + 1);
 }
 __host__ __device__ inline size_t slab_ints(int cap, int Kc) { return (size_t)2 * cap + (size_t)5 * Kc; }
@@ -102,6 +104,7 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
     s.sigma = d; d += sig_elems(cap);
     s.sigma_new = d; d += sig_elems(cap);
     s.H = d; d += sig_elems(cap);
+    s.phit = d; d += (size_t)(nmax + 32) * PHIT_LD;
     s.phi = d; d += (size_t)phi_ld(nmax) * cap;
     s.G = d; d += (size_t)cap * Kc;
     s.xt = d; d += Kc; s.S_in = d; d += Kc; s.Q_in = d; d += Kc; s.S_out = d; d += Kc; s.Q_out = d; d += Kc;
@@ -252,11 +255,11 @@ struct Cand {
     }
     static __device__ inline int sbyte(int w, int b) { return (int)(int8_t)((unsigned)w >> (8 * b)); }
     // element b (0..3) of a 4-row packed word pair loaded from the transposed int8 matrix
+    // (one I2F.F64.S8 with a byte selector per main-effect value: the conversion pipe is otherwise idle next to the DMMAs)
     __device__ inline double from_words(int wi, int wj, int b) const
     {
-        int v = sbyte(wi, b);
-        if (EPIS && i != j) v *= sbyte(wj, b);
-        return small_int_to_double(v);
+        if (EPIS && i != j) return (double)(sbyte(wi, b) * sbyte(wj, b));
+        return (double)(signed char)((unsigned)wi >> (8 * b));
     }
     __device__ inline double at(const int8_t *Xrow) const      // exact: |x| <= 127, products <= 2^14
     {

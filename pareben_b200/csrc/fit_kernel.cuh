@@ -11,16 +11,19 @@
 namespace pareben {
 
 // the persistent batched-fit kernel: one block = one fit at a time, fits pulled from a queue
+#ifndef PAREBEN_MIN_BLOCKS
+#define PAREBEN_MIN_BLOCKS 2
+#endif
 constexpr int FIT_THREADS = FIT_T;     // compile-time maximum (register budget: 2 x 256 or 4 x 128 threads per SM)
 
-constexpr int SWEEP_DOUBLES = SWEEP_SMEM_M * SWEEP_SMEM_M + 2 * SWEEP_SMEM_M;
-constexpr int QUAD_DOUBLES = 2 * KT * LDS_V + 784;
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int SWEEP_DOUBLES = SWEEP_SMEM_M * SWEEP_SMEM_M + 2 * SWEEP_SMEM_M;
+constexpr int QUAD_DOUBLES = cmax(2 * QT * LDS_V + 784, cmax(4096 + 1040, GRAM_PIPE_DOUBLES));
 constexpr int S_BUF_DOUBLES = cmax(cmax(SWEEP_DOUBLES, SV_DOUBLES), cmax(GRAM_DOUBLES, QUAD_DOUBLES));
 constexpr size_t S_BUF_BYTES = (size_t)S_BUF_DOUBLES * sizeof(double);
 
 template <bool EPIS, bool BINOMIAL>
-__global__ void __launch_bounds__(FIT_THREADS, 2)
+__global__ void __launch_bounds__(FIT_THREADS, PAREBEN_MIN_BLOCKS)
 eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_tasks, int *queue, char *slabs,
                 size_t slab_stride, FitOutputs out)
 {

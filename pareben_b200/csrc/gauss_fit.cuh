@@ -44,7 +44,9 @@ struct GaussState {
 //   colval(r, h)  value of right-hand side r at row h (the caller folds any row weight in)
 //   sq_first      when true, right-hand side 0 is contracted with x^2 instead of x
 //                 (the binomial sum_h w[h] x^2, NEmainEff.c:1728-1729)
-constexpr int KT = 32;            // rows per shared-memory stage
+constexpr int KT = 32;            // rows per shared-memory stage of the contraction (two groups of 16; a larger stage is faster in isolation but
+                                  // its shared memory comes out of the L1 that the latency-bound phases live on)
+constexpr int QT = 32;            // rows per stage of the row-major tiles (quadratic forms)
 constexpr int NT_MAX = 4;         // 8-column B tiles per pass (32 right-hand sides): 16 x 32 accumulators = 32 registers, no spills
 constexpr int MT = 2;             // 8-candidate A tiles per warp
 constexpr int LDS_V = 68;         // leading dimension of a row-major staged tile (quadratic forms): == 4 (mod 16) doubles -> conflict-free B fragments
@@ -52,6 +54,14 @@ constexpr int SIMT_R_MAX = 4;
 constexpr int RCS = 4;            // accumulators per thread in the SIMT path
 constexpr int PF = 8;             // rows of X prefetched per group (SIMT path)
 constexpr int FIT_T = 256;        // threads per block (the tile-production loops are unrolled for it)
+
+// a / b given r = 1/b (correctly rounded): quotient estimate plus one FMA residual correction -- the tail of the
+// division routine without its reciprocal iteration; used where one divisor serves many dividends.
+__device__ inline double div_by(double a, double b, double r)
+{
+    const double q = a * r;
+    return fma(fma(-q, b, a), r, q);
+}
 
 __device__ inline void dmma(double &d0, double &d1, double a, double b)
 {
@@ -66,7 +76,7 @@ template <bool PERM>
 __device__ inline void stage_tile(double *dst, int ldd, const double *__restrict__ V, int ldv, int h0, int r0, int ncol)
 {
     const int ch = ncol >> 1;                  // 16-byte chunks per row
-    for (int idx = threadIdx.x; idx < KT * ch; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < QT * ch; idx += blockDim.x) {
         const int h = idx / ch, q = idx - h * ch;
         const int hp = PERM ? ((h & ~15) | ((h & 3) << 2) | ((h >> 2) & 3)) : h;
         __pipeline_memcpy_async(dst + hp * ldd + 2 * q, V + (size_t)(h0 + h) * ldv + r0 + 2 * q, 16);
@@ -106,7 +116,11 @@ __device__ inline void mma_pass(const FoldData &F, int K, int Kc, int R, int r0,
     const bool weighted = wv != nullptr;
     const int ncol = min(8 * NT, R - r0);                     // live columns of this pass (the rest of the tile is zeroed once)
     auto issue_stage = [&](int st) {
+#ifdef MB_NO_STAGE
+        if (false) {
+#else
         if (st < nstage) {
+#endif
             double *dst = sV + (st % NSTG) * STAGE_DOUBLES;
             const int h0 = st * KT;
             // aligned columns: KT/2 16-byte chunks each
@@ -151,29 +165,35 @@ __device__ inline void mma_pass(const FoldData &F, int K, int Kc, int R, int r0,
         // A fragments of one group of 16 rows.  The transposed training matrix is stored with the rows of every
         // group permuted (physical position 4a + b holds row 4b + a), so the 32-bit word (or the four doubles) at
         // positions 4*gk .. 4*gk+3 holds rows gk, gk+4, gk+8, gk+12: exactly this lane's element of the four k-steps.
-        // int8: the raw words of the next two groups sit in a two-slot ring (slot = group parity, static indices, no
-        // register moves); a slot is converted to doubles when its group becomes current and refilled at once with the
-        // group two ahead, so every load has two groups of DMMAs (>= 1000 cycles) to land.  f64: loaded one group ahead.
+        // int8: the raw words of the next NG groups sit in a ring (slot = group index within its stage: static indices,
+        // no register moves); a slot is converted to doubles when its group becomes current and refilled at once with the
+        // group NG ahead, so every load has NG - 1 groups of DMMAs (> 1500 cycles) to land.  f64: loaded one group ahead.
+        constexpr int NG = KT / 16;                            // groups per stage == ring slots
         double xv[MT][4];
-        int wn[2][MT][2];
+        int wn[NG][MT][2];
+        const int8_t *pa0 = X8 + (size_t)cd0.i * ldt + 4 * gk, *pa1 = X8 + (size_t)cd1.i * ldt + 4 * gk;
+        const int8_t *pj0 = X8 + (size_t)cd0.j * ldt + 4 * gk, *pj1 = X8 + (size_t)cd1.j * ldt + 4 * gk;
         auto fetch8 = [&](int slot, int grp) {
-            const int h = min(16 * grp, Np - 16) + 4 * gk;
-            wn[slot][0][0] = *reinterpret_cast<const int *>(X8 + (size_t)cd0.i * ldt + h);
-            wn[slot][1][0] = *reinterpret_cast<const int *>(X8 + (size_t)cd1.i * ldt + h);
+            const int h = min(16 * grp, Np - 16);
+            wn[slot][0][0] = *reinterpret_cast<const int *>(pa0 + h);
+            wn[slot][1][0] = *reinterpret_cast<const int *>(pa1 + h);
             if (EPIS) {
-                wn[slot][0][1] = *reinterpret_cast<const int *>(X8 + (size_t)cd0.j * ldt + h);
-                wn[slot][1][1] = *reinterpret_cast<const int *>(X8 + (size_t)cd1.j * ldt + h);
+                wn[slot][0][1] = *reinterpret_cast<const int *>(pj0 + h);
+                wn[slot][1][1] = *reinterpret_cast<const int *>(pj1 + h);
             }
         };
-        // make group `grp` current (xv), then start the loads of group grp + 2 into the slot just freed
+        // make group `grp` current (xv), then start the loads of group grp + NG into the slot just freed
         auto advance = [&](int slot, int grp) {
+#ifdef MB_NO_A
+            if (true) { for (int ks = 0; ks < 4; ks++) { xv[0][ks] = 1.0 + gk; xv[1][ks] = 2.0 + gm; } return; }
+#endif
             if (X8) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {
                     xv[0][ks] = cd0.from_words(wn[slot][0][0], EPIS ? wn[slot][0][1] : 0, ks);
                     xv[1][ks] = cd1.from_words(wn[slot][1][0], EPIS ? wn[slot][1][1] : 0, ks);
                 }
-                fetch8(slot, grp + 2);
+                fetch8(slot, grp + NG);
             } else {
                 const int h = min(16 * grp, Np - 16) + 4 * gk;
                 const double2 *p0 = reinterpret_cast<const double2 *>(Xd + (size_t)cd0.i * ldt + h);
@@ -195,47 +215,74 @@ __device__ inline void mma_pass(const FoldData &F, int K, int Kc, int R, int r0,
                 }
             }
         };
-        __syncthreads();                                       // the ring is free (previous round / pass fully consumed)
+        if (rd == 0) {
+            __syncthreads();                                   // the ring is free (previous pass / phase fully consumed)
 #pragma unroll
-        for (int d = 0; d < NSTG - 1; d++) issue_stage(d);
+            for (int d = 0; d < NSTG - 1; d++) issue_stage(d);
+        }
         if (live) {
-            if (X8) { fetch8(0, 0); fetch8(1, 1); }
+            if (X8) {
+#pragma unroll
+                for (int d = 0; d < NG; d++) fetch8(d, d);
+            }
             advance(0, 0);
         }
         for (int st = 0; st < nstage; st++) {
             __pipeline_wait_prior(NSTG - 2);                   // stage st has landed (for this thread's copies)
+#ifndef MB_NO_BARRIER
             __syncthreads();                                   // ... and for everyone's; stage st-1 is fully consumed
+#endif
             issue_stage(st + NSTG - 1);
             const double *buf = sV + (st % NSTG) * STAGE_DOUBLES;
             const double *wrow = buf + 8 * NT_MAX * LDS_C;
             if (live) {
 #pragma unroll
-                for (int g = 0; g < KT / 16; g++) {
+                for (int g = 0; g < NG; g++) {
+                    if (st * KT + 16 * g >= N) break;          // block-uniform: whole groups past the last row are skipped
+                    // group prologue: everything the CUDA cores have to do for these 16 rows (row weights into the A
+                    // operand, the two ride-along sums), so that the 8*NT DMMAs below issue back to back
+                    double aw0[4], aw1[4];
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++) {
                         const int hl = 16 * g + 4 * ks + gk;
-                        const double *bcol = buf + gm * LDS_C + hl;
                         double a0 = xv[0][ks], a1 = xv[1][ks];
-                        double b[NT];
-#pragma unroll
-                        for (int n = 0; n < NT; n++) b[n] = bcol[8 * n * LDS_C];
                         if (weighted) {
                             const double w = wrow[hl], e = wrow[KT + hl];
                             bb0 = fma(a0 * a0, w, bb0); bb1 = fma(a1 * a1, w, bb1);
                             ze0 = fma(a0, e, ze0); ze1 = fma(a1, e, ze1);
                             a0 *= w; a1 *= w;
                         }
+                        aw0[ks] = a0; aw1[ks] = a1;
+                    }
+                    const double *bcol = buf + gm * LDS_C + 16 * g + gk;
+                    double bc[NT], bn[NT];
+#pragma unroll
+                    for (int n = 0; n < NT; n++) bc[n] = bcol[8 * n * LDS_C];
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        if (ks < 3) {
+#pragma unroll
+                            for (int n = 0; n < NT; n++) bn[n] = bcol[8 * n * LDS_C + 4 * (ks + 1)];
+                        }
 #pragma unroll
                         for (int n = 0; n < NT; n++) {
-                            dmma(acc[0][n][0], acc[0][n][1], a0, b[n]);
-                            dmma(acc[1][n][0], acc[1][n][1], a1, b[n]);
+                            dmma(acc[0][n][0], acc[0][n][1], aw0[ks], bc[n]);
+                            dmma(acc[1][n][0], acc[1][n][1], aw1[ks], bc[n]);
                         }
+#pragma unroll
+                        for (int n = 0; n < NT; n++) bc[n] = bn[n];
                     }
-                    advance((g + 1) & 1, st * (KT / 16) + g + 1);      // KT / 16 == 2: the slot index is a compile-time constant
+                    advance((g + 1) % NG, st * NG + g + 1);             // the slot index is a compile-time constant
                 }
             }
         }
         __pipeline_wait_prior(0);
+        // every round streams the same tiles: start the next round's first stages before this round's stores
+        __syncthreads();
+        if (rd + 1 < nround) {
+#pragma unroll
+            for (int d = 0; d < NSTG - 1; d++) issue_stage(d);
+        }
         if (live) {
             if (weighted && r0 == 0) {
                 bb0 += __shfl_xor_sync(0xffffffffu, bb0, 1); bb0 += __shfl_xor_sync(0xffffffffu, bb0, 2);
@@ -248,6 +295,10 @@ __device__ inline void mma_pass(const FoldData &F, int K, int Kc, int R, int r0,
                     if (cb < Kc) { bb_out[cb] = bb1; ze_out[cb] = ze1; }
                 }
             }
+#ifdef MB_NO_EPILOGUE
+            if (acc[0][0][0] == 1.2345e-300)
+#endif
+            {
             // destination rows first (their look-ups are independent loads), then divide and store
             double *rowp[NT][2];
             bool rdiv[NT][2];
@@ -263,13 +314,14 @@ __device__ inline void mma_pass(const FoldData &F, int K, int Kc, int R, int r0,
             for (int t = 0; t < MT; t++) {
                 const int c = (mt0 + t * nw) * 8 + gm;
                 if (c < Kc) {
-                    const double sc = F.scale[c];
+                    const double sc = F.scale[c], isc = 1.0 / sc;
 #pragma unroll
                     for (int n = 0; n < NT; n++)
 #pragma unroll
                         for (int i = 0; i < 2; i++)
-                            if (rowp[n][i]) rowp[n][i][c] = rdiv[n][i] ? acc[t][n][i] / sc : acc[t][n][i];
+                            if (rowp[n][i]) rowp[n][i][c] = rdiv[n][i] ? div_by(acc[t][n][i], sc, isc) : acc[t][n][i];
                 }
+            }
             }
         }
     }
@@ -296,7 +348,7 @@ __device__ inline void contract_mma(const FoldData &F, int K, int Kc, int R, int
 
 // R <= RCS right-hand sides (the single new column of an add): one candidate per thread, the right-hand
 // sides of up to SIMT_ROWS rows held in shared memory (row-major, RCS per row) and broadcast with 32-byte loads.
-constexpr int SIMT_ROWS = (2 * KT * LDS_V) / RCS;
+constexpr int SIMT_ROWS = (2 * QT * LDS_V) / RCS;
 
 template <bool EPIS, class XT, class ColVal, class Dest>
 __device__ inline void contract_simt(const XT *__restrict__ X, int N, int K, int Kc, int R, ColVal colval,
@@ -375,12 +427,84 @@ __device__ inline void contract_x(const FoldData &F, int K, int Kc, int R, int n
     }
 }
 
+// SIMT form of the quadratic forms, used while the active set is small (M <= QUAD_SIMT_M): measured faster than the
+// tensor-core form there (the DMMA form wins by 3-4x at M ~ 200).
+// Quadratic forms of the candidate cache against the active-set inverse:
+//   quad[c] = g_c' SIGMA g_c,  lin[c] = g_c' v      with g_c = G[:, c]   (FullStat*, MainEff.c:1291-1316)
+// SIGMA is first copied to a padded layout (leading dimension ldp, multiple of 8, in `sigp`) so a
+// thread reads 8 consecutive entries of a row with two 32-byte loads; z_p accumulates over j in
+// ascending order and quad over p in ascending order, as the reference's loops do.
+template <class Emit>
+__device__ inline void quad_forms_simt(const Slab &s, const double *sigma, double *sigp_global, int M, int Kc, const double *v,
+                                  double *smem /* >= 4096 + 1040 doubles */, Emit emit)
+{
+    PHASE(PH_QUAD);
+    const int T = blockDim.x;
+    const int ldp = (M + 7) & ~7;
+    // padded copy sigp[j][p] = SIGMA(p, j): in shared memory when it fits (M <= 64), else in the spare SIGMA buffer
+    double *sigp = (M * ldp <= 4096) ? smem : sigp_global;
+    size_t *rowoff = reinterpret_cast<size_t *>(smem + 4096);          // G row offsets: no dependent index load in the hot loop
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < M * ldp; idx += T) {
+        const int j = idx / ldp, p = idx - j * ldp;
+        sigp[idx] = p < M ? sigma[p * M + j] : 0.0;
+    }
+    const bool off_smem = M <= 1040;
+    if (off_smem) for (int j = threadIdx.x; j < M; j += T) rowoff[j] = (size_t)s.grow[j] * Kc;
+    __syncthreads();
+    auto roff = [&](int j) -> size_t { return off_smem ? rowoff[j] : (size_t)s.grow[j] * Kc; };
+    // two candidates per thread share every SIGMA row fetched; four G rows are loaded ahead of their FMAs
+    for (int c0 = 0; c0 < Kc; c0 += 2 * T) {
+        const int ca = c0 + threadIdx.x, cb = ca + T;
+        const bool la = ca < Kc, lb = cb < Kc;
+        const int xa = la ? ca : 0, xb = lb ? cb : 0;
+        double quad_a = 0, lin_a = 0, quad_b = 0, lin_b = 0;
+        for (int p0 = 0; p0 < M; p0 += 8) {
+            double za[8], zb[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { za[q] = 0.0; zb[q] = 0.0; }
+            for (int j = 0; j < M; j += 4) {
+                double ga[4], gb[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const size_t o = roff(min(j + u, M - 1));
+                    ga[u] = s.G[o + xa]; gb[u] = s.G[o + xb];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j + u < M) {
+                        const double4 *row = reinterpret_cast<const double4 *>(sigp + (size_t)(j + u) * ldp + p0);
+                        const double4 a = row[0], b = row[1];
+                        za[0] = fma(ga[u], a.x, za[0]); za[1] = fma(ga[u], a.y, za[1]); za[2] = fma(ga[u], a.z, za[2]); za[3] = fma(ga[u], a.w, za[3]);
+                        za[4] = fma(ga[u], b.x, za[4]); za[5] = fma(ga[u], b.y, za[5]); za[6] = fma(ga[u], b.z, za[6]); za[7] = fma(ga[u], b.w, za[7]);
+                        zb[0] = fma(gb[u], a.x, zb[0]); zb[1] = fma(gb[u], a.y, zb[1]); zb[2] = fma(gb[u], a.z, zb[2]); zb[3] = fma(gb[u], a.w, zb[3]);
+                        zb[4] = fma(gb[u], b.x, zb[4]); zb[5] = fma(gb[u], b.y, zb[5]); zb[6] = fma(gb[u], b.z, zb[6]); zb[7] = fma(gb[u], b.w, zb[7]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (p0 + q < M) {
+                    const size_t o = roff(p0 + q);
+                    const double gpa = s.G[o + xa], gpb = s.G[o + xb];
+                    quad_a = fma(za[q], gpa, quad_a); quad_b = fma(zb[q], gpb, quad_b);
+                    if (v) { lin_a = fma(gpa, v[p0 + q], lin_a); lin_b = fma(gpb, v[p0 + q], lin_b); }
+                }
+            }
+        }
+        if (la) emit(ca, quad_a, lin_a);
+        if (lb) emit(cb, quad_b, lin_b);
+    }
+    __syncthreads();
+}
+
+
 // Quadratic forms of the candidate cache against the active-set inverse:
 //   quad[c] = g_c' SIGMA g_c,  lin[c] = g_c' v      with g_c = G[:, c]   (FullStat*, MainEff.c:1291-1316)
 // Tensor-core form: Z = G' SIGMA is a (Kc x M) x (M x M) product -- A fragments are 8 candidates x 4 cache
 // rows read straight from G (through the row permutation), B fragments come from a zero-padded copy of
 // SIGMA in shared memory -- and quad[c] = sum_p Z[c][p] G[p][c] is folded into the accumulator epilogue.
-// For M <= 2*KT the padded SIGMA stays resident in shared memory for the whole call; larger matrices are
+// For M <= 2*QT the padded SIGMA stays resident in shared memory for the whole call; larger matrices are
 // streamed through the same double buffer in 64-column chunks from a padded copy in the spare SIGMA buffer.
 // Every candidate goes through the identical sequence of operations (duplicate columns tie exactly).
 template <int NT>
@@ -390,7 +514,7 @@ __device__ inline void quad_chunk(const double *__restrict__ G, const size_t *ro
 {
     const int lane = threadIdx.x & 31;
     const int gm = lane >> 2, gk = lane & 3;
-    const int nstage = (M + KT - 1) / KT;
+    const int nstage = (M + QT - 1) / QT;
     auto roff = [&](int j) -> size_t { return rowoff ? rowoff[j] : (size_t)grow[j] * Kc; };
     double acc[MT][NT][2];
 #pragma unroll
@@ -410,13 +534,13 @@ __device__ inline void quad_chunk(const double *__restrict__ G, const size_t *ro
     if (live) { fetch(xv, 0); fetch(xn, 16); }
     if (!resident) { __pipeline_wait_prior(0); __syncthreads(); }
     for (int st = 0; st < nstage; st++) {
-        const double *buf = sV + (st & 1) * (KT * LDS_V);
-        if (!resident && st + 1 < nstage) stage_tile<false>(sV + ((st + 1) & 1) * (KT * LDS_V), LDS_V, sigp, ldp, (st + 1) * KT, p0, 8 * NT);
+        const double *buf = sV + (st & 1) * (QT * LDS_V);
+        if (!resident && st + 1 < nstage) stage_tile<false>(sV + ((st + 1) & 1) * (QT * LDS_V), LDS_V, sigp, ldp, (st + 1) * QT, p0, 8 * NT);
         if (live) {
 #pragma unroll
-            for (int g = 0; g < KT / 16; g++) {
-                if (st * KT + 16 * g < M) {                    // warp-uniform: groups past the last cache row are skipped
-                    fetch(xn2, st * KT + 16 * (g + 2));
+            for (int g = 0; g < QT / 16; g++) {
+                if (st * QT + 16 * g < M) {                    // warp-uniform: groups past the last cache row are skipped
+                    fetch(xn2, st * QT + 16 * (g + 2));
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++) {
                         const double *brow = buf + (16 * g + 4 * ks + gk) * LDS_V + gm + (resident ? p0 : 0);   // the resident tile holds every column
@@ -454,16 +578,16 @@ __device__ inline void quad_chunk(const double *__restrict__ G, const size_t *ro
 }
 
 template <class Emit>
-__device__ inline void quad_forms(const Slab &s, const double *sigma, double *sigp_global, int M, int Kc, const double *v,
-                                  double *smem /* >= 2*KT*LDS_V + 784 doubles */, Emit emit)
+__device__ inline void quad_forms_mma(const Slab &s, const double *sigma, double *sigp_global, int M, int Kc, const double *v,
+                                      double *smem /* >= 2*QT*LDS_V + 784 doubles */, Emit emit)
 {
     PHASE(PH_QUAD);
     const int T = blockDim.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
     const int gm = lane >> 2, gk = lane & 3;
-    const int ldp = (M + 7) & ~7, Mp = ((M + KT - 1) / KT) * KT;
-    const bool resident = Mp <= 2 * KT;
-    size_t *rowoff = M <= 784 ? reinterpret_cast<size_t *>(smem + 2 * KT * LDS_V) : nullptr;
+    const int ldp = (M + 7) & ~7, Mp = ((M + QT - 1) / QT) * QT;
+    const bool resident = Mp <= 2 * QT;
+    size_t *rowoff = M <= 784 ? reinterpret_cast<size_t *>(smem + 2 * QT * LDS_V) : nullptr;
     __syncthreads();
     // zero-padded copy sigp[j][p] = SIGMA(p, j): straight into the shared tile layout when resident
     if (resident) {
@@ -512,6 +636,15 @@ __device__ inline void quad_forms(const Slab &s, const double *sigma, double *si
     __syncthreads();
 }
 
+constexpr int QUAD_SIMT_M = 64;
+template <class Emit>
+__device__ inline void quad_forms(const Slab &s, const double *sigma, double *sigp_global, int M, int Kc, const double *v,
+                                  double *smem, Emit emit)
+{
+    if (M <= QUAD_SIMT_M) quad_forms_simt(s, sigma, sigp_global, M, Kc, v, smem, emit);
+    else quad_forms_mma(s, sigma, sigp_global, M, Kc, v, smem, emit);
+}
+
 // dot products of active columns with a vector: out[i] = sum_h phi_i[h] * v[h], one warp per i.
 __device__ inline void phi_dot(const double *phi, int N, int M, const double *v, double *out, double scale)
 {
@@ -519,7 +652,6 @@ __device__ inline void phi_dot(const double *phi, int N, int M, const double *v,
     for (int i = wid; i < M; i += nw) {
         const double *p = phi + (size_t)i * LD;
         double z = 0;
-#pragma unroll 8
         for (int h = lane; h < N; h += 32) z = fma(p[h], v[h], z);
         z = warp_sum(z);
         if (lane == 0) out[i] = z * scale;
@@ -735,6 +867,91 @@ __device__ inline void gram_mma(const double *__restrict__ phi, int N, int LD, i
                 out(j, k, z);
             }
         }
+    }
+    __syncthreads();
+}
+
+// Pipelined Gram matrix for at most 64 active columns, from the ROW-major copy PHIt (leading dimension
+// PHIT_LD = 64):  H(j, k) = sum_h (phit[h][j] * w[h]) * phit[h][k],  j <= k.
+// Tiles of 32 rows (16 KB) are streamed with cp.async, double-buffered, so the copy of tile t+1
+// overlaps the FMAs of tile t and there is one barrier per tile (gram_tiled pays two barriers and
+// an exposed global load per tile).  Register blocks, row splitting and the fixed-order combination
+// of partial sums are as in gram_tiled.   smem: 2 * 32 * 64 + 64 doubles (w tiles).
+constexpr int GP_ROWS = 32;
+constexpr int GRAM_PIPE_DOUBLES = 2 * GP_ROWS * PHIT_LD + 2 * GP_ROWS;
+
+template <class Out>
+__device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, const double *__restrict__ w,
+                                 double *sm, Out out)
+{
+    PHASE(PH_GRAM);
+    const int T = blockDim.x;
+    double *tiles = sm, *wt = sm + 2 * GP_ROWS * PHIT_LD;
+    const int ntile = (N + GP_ROWS - 1) / GP_ROWS;
+    const int nb = (M + 3) >> 2, nblk = nb * (nb + 1) / 2;
+    const int nsplit = max(1, min(min(T, 256) / nblk, 8));
+    const int blk = threadIdx.x % nblk, split = threadIdx.x / nblk;
+    const bool active = threadIdx.x < nblk * nsplit;
+    int bj = 0, bk = blk;
+    { int rem = blk; while (rem >= nb - bj) { rem -= nb - bj; bj++; } bk = bj + rem; }
+    const int rps = (GP_ROWS + nsplit - 1) / nsplit;            // rows of a tile per split
+    auto stage = [&](int t) {
+        if (t < ntile) {
+            double *dst = tiles + (t & 1) * (GP_ROWS * PHIT_LD);
+            const int h0 = t * GP_ROWS;
+            for (int idx = threadIdx.x; idx < GP_ROWS * (PHIT_LD / 2); idx += T) {
+                const int hl = idx >> 5, q = idx & 31;          // 32 16-byte pieces per row
+                __pipeline_memcpy_async(dst + hl * PHIT_LD + 2 * q, phit + (size_t)min(h0 + hl, N - 1) * PHIT_LD + 2 * q, 16);
+            }
+            if (threadIdx.x < GP_ROWS) wt[(t & 1) * GP_ROWS + threadIdx.x] = (h0 + (int)threadIdx.x < N) ? (w ? w[h0 + threadIdx.x] : 1.0) : 0.0;
+        }
+        __pipeline_commit();
+    };
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+    __syncthreads();
+    stage(0);
+    for (int t = 0; t < ntile; t++) {
+        __pipeline_wait_prior(0);
+        __syncthreads();                                         // tile t visible; everyone finished tile t-1
+        stage(t + 1);
+        if (active) {
+            const double *tile = tiles + (t & 1) * (GP_ROWS * PHIT_LD), *wv = wt + (t & 1) * GP_ROWS;
+            const int hb = split * rps, he = min(hb + rps, GP_ROWS);
+#pragma unroll 2
+            for (int hl = hb; hl < he; hl++) {
+                const double4 a4 = *reinterpret_cast<const double4 *>(tile + hl * PHIT_LD + 4 * bj);
+                const double4 b4 = *reinterpret_cast<const double4 *>(tile + hl * PHIT_LD + 4 * bk);
+                const double ww = wv[hl];                        // rows past N carry weight 0
+                const double av[4] = {a4.x * ww, a4.y * ww, a4.z * ww, a4.w * ww}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+            }
+        }
+    }
+    __pipeline_wait_prior(0);
+    __syncthreads();                                             // tiles are dead: reuse the buffer for the partial sums
+    if (active) {
+        double *dst = sm + ((size_t)split * nblk + blk) * 16;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) dst[a * 4 + b] = acc[a][b];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nblk * 16; idx += T) {
+        const int b2 = idx >> 4, e = idx & 15, a = e >> 2, b = e & 3;
+        double z = 0.0;
+        for (int sp = 0; sp < nsplit; sp++) z += sm[((size_t)sp * nblk + b2) * 16 + e];
+        int cj = 0, ck = b2;
+        { int rem = b2; while (rem >= nb - cj) { rem -= nb - cj; cj++; } ck = cj + rem; }
+        const int j = 4 * cj + a, k = 4 * ck + b;
+        if (j < M && k < M && j <= k) out(j, k, z);
     }
     __syncthreads();
 }
@@ -1147,7 +1364,6 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                 { PHASE(PH_LOGLIK);
                 for (int h = threadIdx.x; h < N; h += T) {
                     double pm = 0;
-#pragma unroll 8
                     for (int j = 0; j < M; j++) pm = fma(s.phi[(size_t)j * LD + h], s.mu[j], pm);
                     const double e = s.t[h] - pm;
                     ee = fma(e, e, ee);

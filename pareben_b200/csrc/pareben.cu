@@ -335,7 +335,7 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
             else scales_kernel<false><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
             F.Xtr = Xtr; F.ytr = ytr; F.Xte = Xte; F.yte = yte; F.scale = scale; F.Xtr8 = nullptr;
             F.XT8 = nullptr; F.XTd = nullptr;
-            F.ldt = (F.ntr + 31) & ~31;
+            F.ldt = (F.ntr + 63) & ~63;      // whole stages of the contraction (KT = 64 rows)
             {
                 const dim3 tg((F.ldt + 31) / 32, (k + 31) / 32);
                 if (small_int) {
