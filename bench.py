@@ -275,7 +275,8 @@ def run_gpu(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": 1e3 * e2e_t / args.steps},
                 "gpu_launches": int(args.steps),
-                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA mma.sync.m8n8k4.f64 for the contraction, DFMA elsewhere)",
+                             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                              "traffic": traffic, "kernel": "eben_fit_kernel<binomial,main>",
                              "algorithmic_flops_per_launch": avg_fl, "launch_ms": avg_ms,
                              "peak_source": f"on-box probe at bench start: DFMA {peak_dfma:.1f}, DMMA {peak_dmma:.1f} TFLOP/s "

@@ -1,8 +1,9 @@
 #!/bin/bash
-# Round-end style run: tests, smoke, bench (+launch list), one full-size ncu capture for DRAM traffic
+# Round-end style run: tests, smoke, parity report, bench (+ reference arm), ncu launch list, one full-size ncu capture
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { tail -20 gpurun_out/build.log; exit 1; }
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv,noheader
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 300 python scripts/parity_report.py > gpurun_out/parity_stdout.log 2>&1; tail -7 gpurun_out/parity_stdout.log
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json

@@ -1,0 +1,111 @@
+"""GPU suite (-m gpu), part 2: shapes and storage paths the golden fixtures do not reach.
+
+Every case is checked fit by fit against whichever oracle library is present on the box
+(oracle/_ref = the reference's own C compiled unmodified, else the C restatement), on seeded
+inputs generated here.  Scaled-down stand-ins for BASELINE configs 3-5:
+  * a wide main-effect design (K >> N, config 3's shape at 1/10 scale),
+  * Epis designs with a few thousand pair candidates (configs 4/5 at the scale the CPU oracle
+    finishes in seconds), Gaussian and binomial,
+  * a real-valued (non-genotype) design, which takes the f64 operand path of the tensor-core
+    contraction instead of the int8 one.
+Tolerances as in test_gpu_parity.py: 1e-8 relative on Gaussian fold errors, 1e-7 on binomial
+ones (see the note there), support sizes identical.
+"""
+import numpy as np
+import pytest
+
+from oracle import rlayer as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb(built):
+    import pareben_b200 as pb
+    if pb.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu suite must run on the B200 box")
+    return pb
+
+
+def _check(pb, X, y, n_folds, lam, alpha, epis, prior, rtol, folds_to_check=None):
+    lib = R.fit_lib(R.available_kind())
+    folds = R.assign_to_folds(X.shape[0], n_folds)
+    err, st, ns = pb.cv_grid(X, y, folds, n_folds, alpha, lam, epis=epis, prior=prior)
+    assert np.all(st == 0)
+    worst, biggest = 0.0, 0
+    for i in range(lam.size):
+        for f in (folds_to_check or range(1, n_folds + 1)):
+            e, fit = R.fit_one(X, y, folds, f, lam[i], alpha[i], epis, prior, lib)
+            m = 0 if fit.weight[0, 0] == 0 else fit.weight.shape[0]
+            assert ns[i, f - 1] == m, f"support size differs at lambda={lam[i]}, alpha={alpha[i]}, fold {f}: {ns[i, f - 1]} vs {m}"
+            worst = max(worst, abs(err[i, f - 1] - e) / max(abs(e), 1e-300))
+            biggest = max(biggest, m)
+    assert worst < rtol, f"max relative fold-error difference {worst:.3e}"
+    return biggest
+
+
+def _genotypes(rng, n, k, block=25, copy=0.85):
+    """Ternary design with neighbour correlation (blocks of linked loci), like the bundled BASIS."""
+    X = rng.choice([-1.0, 0.0, 1.0], size=(n, k), p=[0.25, 0.5, 0.25])
+    for j in range(1, k):
+        if j % block:
+            keep = rng.random(n) < copy
+            X[keep, j] = X[keep, j - 1]
+    return X
+
+
+def test_wide_main_effect_design(pb):
+    """Config-3 shape at reduced scale: K = 3000 >> N = 300, +-1/0 genotypes, Gaussian main effects."""
+    rng = np.random.default_rng(20260101)
+    n, k = 300, 3000
+    X = _genotypes(rng, n, k)
+    beta = np.zeros(k); beta[rng.choice(k, 12, replace=False)] = rng.normal(0, 2.0, 12)
+    y = 100 + X @ beta + rng.normal(0, 3.0, n)
+    lam = np.array([2.0, 0.5, 0.12, 0.03]); alpha = np.array([1.0, 0.6, 0.3, 0.05])
+    m = _check(pb, X, y, 3, lam, alpha, False, "gaussian", 1e-8)
+    assert m >= 10          # the small-lambda fits really do build a non-trivial active set
+
+
+def test_epis_gaussian_thousands_of_pairs(pb):
+    """Config-4/5 path at oracle-sized scale: 60 loci -> 1,830 candidates generated on the fly."""
+    rng = np.random.default_rng(7)
+    n, k = 200, 60
+    X = _genotypes(rng, n, k, block=10)
+    y = 50 + 2.5 * X[:, 3] - 2.0 * X[:, 40] + 3.0 * X[:, 7] * X[:, 22] - 2.5 * X[:, 31] * X[:, 55] + rng.normal(0, 2.0, n)
+    lam = np.array([1.5, 0.4, 0.1]); alpha = np.array([1.0, 0.5, 0.1])
+    _check(pb, X, y, 3, lam, alpha, True, "gaussian", 1e-8)
+
+
+def test_epis_binomial_thousands_of_pairs(pb):
+    rng = np.random.default_rng(8)
+    n, k = 200, 40
+    X = _genotypes(rng, n, k, block=10)
+    eta = 1.2 * X[:, 5] - 1.0 * X[:, 17] + 1.5 * X[:, 2] * X[:, 30]
+    y = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float)
+    lam = np.array([0.5, 0.12]); alpha = np.array([1.0, 0.4])
+    _check(pb, X, y, 2, lam, alpha, True, "binomial", 1e-7)
+
+
+def test_real_valued_design_uses_f64_operands(pb):
+    """Non-integer BASIS: no int8 copy exists, the contraction reads the transposed f64 matrix."""
+    rng = np.random.default_rng(12)
+    n, k = 150, 60
+    X = rng.normal(size=(n, k))
+    X[:, 10] = 0.6 * X[:, 3] + 0.8 * X[:, 10]                 # some collinearity
+    y = 10 + X[:, :6] @ np.array([2.0, -1.5, 1.0, 0.8, -0.6, 0.5]) + rng.normal(0, 1.0, n)
+    lam = np.array([1.0, 0.2, 0.04]); alpha = np.array([1.0, 0.5, 0.1])
+    m = _check(pb, X, y, 3, lam, alpha, False, "gaussian", 1e-8)
+    assert m > 4            # more than SIMT_R_MAX right-hand sides: the tensor-core path ran
+    yb = (rng.random(n) < 1 / (1 + np.exp(-(X[:, 0] - X[:, 1] + 0.5 * X[:, 2])))).astype(float)
+    _check(pb, X, yb, 3, np.array([0.3, 0.05]), np.array([1.0, 0.3]), False, "binomial", 1e-7)
+    # pairs of real-valued loci
+    _check(pb, X[:, :14], y, 2, np.array([0.8, 0.1]), np.array([0.9, 0.2]), True, "gaussian", 1e-8)
+
+
+def test_odd_row_counts_and_tiny_folds(pb):
+    """Row counts that are not multiples of the 16-row MMA groups / 4-row PHI padding, in every fold."""
+    rng = np.random.default_rng(21)
+    for n, k, nf in ((37, 30, 2), (131, 75, 7)):
+        X = _genotypes(rng, n, k, block=8)
+        y = 5 + 1.5 * X[:, 1] - X[:, k // 2] + rng.normal(0, 1.0, n)
+        _check(pb, X, y, nf, np.array([0.6, 0.05]), np.array([1.0, 0.25]), False, "gaussian", 1e-8)
