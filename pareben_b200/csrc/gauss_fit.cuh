@@ -698,6 +698,82 @@ __device__ inline bool sweep_core(double *a, int M, double *colbuf)
     return ok;
 }
 
+// Panel variant of sweep_core for matrices that do not fit in registers (M > SWEEP_SMEM_M): NB pivots per pass
+// over the matrix instead of one.  Phase A sweeps the NB pivot columns themselves inside shared memory (saving
+// each pivot's pre-update column C_p and reciprocal); phase B then applies the NB rank-1 updates to every other
+// column with ONE global read and write per element.  Every element sees exactly the operations of sweep_core in
+// the same order, so the result is bit-identical; global traffic and block barriers per element drop by NB.
+//   sm: SWEEP_PANEL_DOUBLES doubles
+constexpr int SWEEP_PANEL_DOUBLES = 5120;
+
+__device__ inline bool sweep_panel(double *a, int M, double *sm)
+{
+    const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    const int Mp = (M + 3) & ~3;
+    int NB = 8;
+    while (NB > 1 && 2 * NB * Mp + NB > SWEEP_PANEL_DOUBLES) NB >>= 1;
+    double *Pn = sm, *C = sm + NB * Mp, *dv = C + NB * Mp;
+    bool ok = true;
+    for (int k0 = 0; k0 < M; k0 += NB) {
+        const int nb = min(NB, M - k0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nb * M; idx += T) {
+            const int q = idx / M, i = idx - q * M;
+            Pn[q * Mp + i] = a[(size_t)(k0 + q) * M + i];
+        }
+        // phase A: the pivots of this panel, applied to the panel's own columns
+        for (int p = 0; p < nb; p++) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < M; i += T) C[p * Mp + i] = Pn[p * Mp + i];
+            __syncthreads();
+            const int k = k0 + p;
+            const double *cp = C + p * Mp;
+            const double d = cp[k];
+            if (!(d > 0.0)) { ok = false; break; }        // uniform: every thread reads the same value
+            const double dinv = 1.0 / d;
+            if (threadIdx.x == 0) dv[p] = dinv;
+            for (int idx = threadIdx.x; idx < nb * M; idx += T) {
+                const int q = idx / M, i = idx - q * M, j = k0 + q;
+                const double cj = cp[j];
+                double v;
+                if (i == k && j == k) v = -dinv;
+                else if (i == k) v = cj * dinv;
+                else if (j == k) v = cp[i] * dinv;
+                else v = Pn[q * Mp + i] - (cp[i] * cj) * dinv;
+                Pn[q * Mp + i] = v;
+            }
+        }
+        if (!ok) break;
+        __syncthreads();
+        // phase B: the same nb pivots, in order, applied to every column outside the panel
+        for (int j = wid; j < M; j += nw) {
+            if (j >= k0 && j < k0 + nb) continue;         // warp-uniform
+            double cj[8], di[8];
+#pragma unroll
+            for (int p = 0; p < 8; p++) { cj[p] = p < nb ? C[p * Mp + j] : 0.0; di[p] = p < nb ? dv[p] : 0.0; }
+            double *col = a + (size_t)j * M;
+#pragma unroll 2
+            for (int i = lane; i < M; i += 32) {
+                double v = col[i];
+#pragma unroll
+                for (int p = 0; p < 8; p++) {
+                    if (p < nb) {
+                        if (i == k0 + p) v = cj[p] * di[p];
+                        else v = v - (C[p * Mp + i] * cj[p]) * di[p];
+                    }
+                }
+                col[i] = v;
+            }
+        }
+        for (int idx = threadIdx.x; idx < nb * M; idx += T) {
+            const int q = idx / M, i = idx - q * M;
+            a[(size_t)(k0 + q) * M + i] = Pn[q * Mp + i];
+        }
+    }
+    __syncthreads();
+    return ok;
+}
+
 // Register-resident variant for M <= 64 and 256 threads: thread (warp w, lane l) owns rows {l, l+32}
 // x columns {w, w+8, ..., w+56} = 16 entries kept in registers across all M pivots; only the pivot
 // column travels through shared memory (2 x 64 doubles, double-buffered), one barrier per pivot.
@@ -767,7 +843,7 @@ __device__ inline bool spd_inverse_sweep(double *a, int M, double *colk, const S
     if (sm && M <= SWEEP_SMEM_M && T == 256) {
         ok = sweep_regs(a, M, sm);
     } else {
-        ok = sweep_core(a, M, colk);          // colk: 2*(cap+1) doubles in the slab
+        ok = sm ? sweep_panel(a, M, sm) : sweep_core(a, M, colk);          // colk: 2*(cap+1) doubles in the slab
         if (ok) for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -a[idx];
     }
     __syncthreads();
