@@ -19,7 +19,7 @@ constexpr int FIT_THREADS = FIT_T;     // compile-time maximum (register budget:
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 constexpr int SWEEP_DOUBLES = SWEEP_SMEM_M * SWEEP_SMEM_M + 2 * SWEEP_SMEM_M;
 constexpr int QUAD_DOUBLES = cmax(2 * QT * LDS_V + 784, cmax(4096 + 1040, GRAM_PIPE_DOUBLES));
-constexpr int S_BUF_DOUBLES = cmax(cmax(cmax(SWEEP_DOUBLES, SWEEP_PANEL_DOUBLES), SV_DOUBLES), cmax(GRAM_DOUBLES, QUAD_DOUBLES));
+constexpr int S_BUF_DOUBLES = cmax(cmax(cmax(SWEEP_DOUBLES, SWEEP_PANEL_DOUBLES), cmax(SV_DOUBLES, COL_MAX_ROWS)), cmax(GRAM_DOUBLES, QUAD_DOUBLES));
 constexpr size_t S_BUF_BYTES = (size_t)S_BUF_DOUBLES * sizeof(double);
 
 template <bool EPIS, bool BINOMIAL>

@@ -410,6 +410,65 @@ __device__ inline void contract_simt(const XT *__restrict__ X, int N, int K, int
     __syncthreads();
 }
 
+// One right-hand side (the new column of an add, the most frequent contraction of a Gaussian fit): a WARP per
+// candidate over the transposed training matrix.  The right-hand side sits in shared memory in the matrix's
+// permuted row order; a lane takes 4 consecutive positions per 128 (one 32-bit word of int8 codes, or four
+// doubles), keeps one partial sum per position and the warp combines them in a fixed order -- 4x fewer
+// instructions than a thread per candidate, and the loads of two candidates are in flight together.
+// Same arithmetic sequence for every candidate (duplicates tie exactly).
+constexpr int COL_MAX_ROWS = 5120;
+
+template <bool EPIS, class ColVal, class Dest>
+__device__ inline void contract_col(const FoldData &F, int K, int Kc, ColVal colval, Dest dest, double *sV)
+{
+    const int N = F.ntr, ldt = F.ldt, T = blockDim.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    const int8_t *__restrict__ X8 = F.XT8;
+    const double *__restrict__ Xd = F.XTd;
+    __syncthreads();
+    PHASE(PH_CONTRACT);
+    for (int pos = threadIdx.x; pos < ldt; pos += T) {
+        const int h = (pos & ~15) | ((pos & 3) << 2) | ((pos >> 2) & 3);          // row stored at this position (see mma_pass)
+        sV[pos] = h < N ? colval(0, h) : 0.0;
+    }
+    __syncthreads();
+    bool dv = false;
+    double *row = dest(0, dv);
+    auto partial = [&](const Cand<EPIS> &cd, int p4, double (&z)[4]) {
+        const double4 v = *reinterpret_cast<const double4 *>(sV + p4);
+        double x[4];
+        if (X8) {
+            const int wi = *reinterpret_cast<const int *>(X8 + (size_t)cd.i * ldt + p4);
+            const int wj = (EPIS && cd.i != cd.j) ? *reinterpret_cast<const int *>(X8 + (size_t)cd.j * ldt + p4) : 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) x[b] = cd.from_words(wi, wj, b);
+        } else {
+            const double2 *pi = reinterpret_cast<const double2 *>(Xd + (size_t)cd.i * ldt + p4);
+            const double2 a = pi[0], c = pi[1];
+            x[0] = a.x; x[1] = a.y; x[2] = c.x; x[3] = c.y;
+            if (EPIS && cd.i != cd.j) {
+                const double2 *pj = reinterpret_cast<const double2 *>(Xd + (size_t)cd.j * ldt + p4);
+                const double2 e = pj[0], f = pj[1];
+                x[0] *= e.x; x[1] *= e.y; x[2] *= f.x; x[3] *= f.y;
+            }
+        }
+        z[0] = fma(x[0], v.x, z[0]); z[1] = fma(x[1], v.y, z[1]); z[2] = fma(x[2], v.z, z[2]); z[3] = fma(x[3], v.w, z[3]);
+    };
+    for (int c0 = wid; c0 < Kc; c0 += 2 * nw) {
+        const int c1 = c0 + nw;
+        const bool two = c1 < Kc;
+        Cand<EPIS> cda(c0, K), cdb(two ? c1 : c0, K);
+        double za[4] = {0.0, 0.0, 0.0, 0.0}, zb[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int p4 = 4 * lane; p4 < ldt; p4 += 128) { partial(cda, p4, za); partial(cdb, p4, zb); }
+        const double ta = warp_sum((za[0] + za[1]) + (za[2] + za[3])), tb = warp_sum((zb[0] + zb[1]) + (zb[2] + zb[3]));
+        if (lane == 0) {
+            row[c0] = dv ? ta / F.scale[c0] : ta;
+            if (two) row[c1] = dv ? tb / F.scale[c1] : tb;
+        }
+    }
+    __syncthreads();
+}
+
 // Dispatch on the number of right-hand sides (and, in the SIMT path, on the storage type of the training matrix).
 //   col(r)        base pointer of right-hand side r (see mma_pass); the first n_aligned are 16-byte aligned columns
 //   dest(r, div)  destination row of right-hand side r; div set when the result is divided by the column norm
@@ -418,7 +477,9 @@ template <bool EPIS, class Col, class Dest>
 __device__ inline void contract_x(const FoldData &F, int K, int Kc, int R, int n_aligned, Col col, Dest dest, double *sV,
                                   const double *wv = nullptr, const double *ev = nullptr, double *bb_out = nullptr, double *ze_out = nullptr)
 {
-    if (R <= SIMT_R_MAX && !bb_out) {
+    if (R == 1 && !bb_out && F.ldt <= COL_MAX_ROWS) {
+        contract_col<EPIS>(F, K, Kc, [&](int r, int h) { const double v = col(r)[h]; return wv ? v * wv[h] : v; }, dest, sV);
+    } else if (R <= SIMT_R_MAX && !bb_out) {
         auto colval = [&](int r, int h) { const double v = col(r)[h]; return wv ? v * wv[h] : v; };
         if (F.Xtr8) contract_simt<EPIS, int8_t>(F.Xtr8, F.ntr, K, Kc, R, colval, dest, F.scale, sV, false);
         else contract_simt<EPIS, double>(F.Xtr, F.ntr, K, Kc, R, colval, dest, F.scale, sV, false);

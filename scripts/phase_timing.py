@@ -40,5 +40,8 @@ with pb.Problem(X, y, folds, nf, False, prior) as p:
         print("  longest fits (ms, lambda, alpha, start ms):", [(round(dur[i],1), float(l[i]), float(a[i]), round(float(t0[i]-start)*1e-6,1)) for i in order[:5]])
         lastend = np.array([ (t1[blk==b].max()-start)*1e-6 for b in range(blk.max()+1)])
         print(f"  block finish times ms: min {lastend.min():.1f} median {np.median(lastend):.1f} max {lastend.max():.1f}")
+        err, st, ns, it = p.run_fits(fold, a, l)
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savez_compressed(f"gpurun_out/trace_{prior}.npz", dur_ms=dur, start_ms=(t0 - start).astype(float) * 1e-6, block=blk, lam=l, alpha=a, fold=fold, n_sel=ns, n_iter=it)
     for nm, c, k in zip(names, cyc, calls):
         print(f"  {nm:30s} {c:.3e}  {100*c/total_block_cycles:5.1f} % of block time   calls {k:.0f}  cycles/call {c/max(k,1):.0f}")
