@@ -760,27 +760,35 @@ __device__ inline bool sweep_core(double *a, int M, double *colbuf)
 }
 
 // Panel variant of sweep_core for matrices that do not fit in registers (M > SWEEP_SMEM_M): NB pivots per pass
-// over the matrix instead of one.  Phase A sweeps the NB pivot columns themselves inside shared memory (saving
-// each pivot's pre-update column C_p and reciprocal); phase B then applies the NB rank-1 updates to every other
-// column with ONE global read and write per element.  Every element sees exactly the operations of sweep_core in
-// the same order, so the result is bit-identical; global traffic and block barriers per element drop by NB.
+// over the matrix instead of one.  Phase A sweeps the NB pivot columns themselves inside shared memory with the
+// one-pivot formulas (saving each pivot's pre-update column C_p and reciprocal); phase B applies the NB rank-1
+// updates to the rest of the matrix as ONE rank-NB update on the FP64 tensor cores:
+//     a(i, j) -= sum_p C_p[i] * (C_p[j] / d_p)          8 x 8 tiles, two DMMAs per tile for NB = 8,
+// lower triangle only, mirrored on store so the matrix stays exactly symmetric; the rows of the panel's pivots are
+// the mirror image of the swept panel columns.  Global traffic and block barriers per element drop by NB and the
+// update runs at tensor-core rate instead of ~7 instructions per element and pivot.
 //   sm: SWEEP_PANEL_DOUBLES doubles
 constexpr int SWEEP_PANEL_DOUBLES = 5120;
 
 __device__ inline bool sweep_panel(double *a, int M, double *sm)
 {
     const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
-    const int Mp = (M + 3) & ~3;
+    const int gm = lane >> 2, gk = lane & 3;
+    const int Mp = ((M + 7) & ~7) + 4;                    // row stride of the panel arrays (tiles may read up to 7 past M)
     int NB = 8;
-    while (NB > 1 && 2 * NB * Mp + NB > SWEEP_PANEL_DOUBLES) NB >>= 1;
-    double *Pn = sm, *C = sm + NB * Mp, *dv = C + NB * Mp;
+    while (NB > 2 && 3 * NB * Mp + NB > SWEEP_PANEL_DOUBLES) NB >>= 1;
+    const int KS = (NB + 3) >> 2;                         // k-steps of the rank-NB update (NB = 2 is padded to 4 with zero rows)
+    const int NBp = 4 * KS;
+    double *Pn = sm, *C = sm + NBp * Mp, *D = C + NBp * Mp, *dv = D + NBp * Mp;
+    const int nt = (M + 7) >> 3, ntile = nt * (nt + 1) / 2;
     bool ok = true;
     for (int k0 = 0; k0 < M; k0 += NB) {
         const int nb = min(NB, M - k0);
         __syncthreads();
-        for (int idx = threadIdx.x; idx < nb * M; idx += T) {
-            const int q = idx / M, i = idx - q * M;
-            Pn[q * Mp + i] = a[(size_t)(k0 + q) * M + i];
+        for (int idx = threadIdx.x; idx < NBp * Mp; idx += T) {
+            const int q = idx / Mp, i = idx - q * Mp;
+            Pn[idx] = (q < nb && i < M) ? a[(size_t)(k0 + q) * M + i] : 0.0;
+            C[idx] = 0.0; D[idx] = 0.0;                   // rows past nb and entries past M contribute nothing to the update
         }
         // phase A: the pivots of this panel, applied to the panel's own columns
         for (int p = 0; p < nb; p++) {
@@ -793,6 +801,7 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
             if (!(d > 0.0)) { ok = false; break; }        // uniform: every thread reads the same value
             const double dinv = 1.0 / d;
             if (threadIdx.x == 0) dv[p] = dinv;
+            for (int i = threadIdx.x; i < M; i += T) D[p * Mp + i] = cp[i] * dinv;
             for (int idx = threadIdx.x; idx < nb * M; idx += T) {
                 const int q = idx / M, i = idx - q * M, j = k0 + q;
                 const double cj = cp[j];
@@ -806,29 +815,34 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
         }
         if (!ok) break;
         __syncthreads();
-        // phase B: the same nb pivots, in order, applied to every column outside the panel
-        for (int j = wid; j < M; j += nw) {
-            if (j >= k0 && j < k0 + nb) continue;         // warp-uniform
-            double cj[8], di[8];
+        // phase B: rank-nb update of the lower triangle, mirrored
+        for (int t = wid; t < ntile; t += nw) {
+            int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+            while (ti * (ti + 1) / 2 > t) ti--;
+            while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+            const int tj = t - ti * (ti + 1) / 2;
+            const int i = 8 * ti + gm, j0 = 8 * tj + 2 * gk;          // this lane's elements: (i, j0) and (i, j0 + 1)
+            double c0 = (i < M && j0 < M) ? a[(size_t)j0 * M + i] : 0.0;
+            double c1 = (i < M && j0 + 1 < M) ? a[(size_t)(j0 + 1) * M + i] : 0.0;
 #pragma unroll
-            for (int p = 0; p < 8; p++) { cj[p] = p < nb ? C[p * Mp + j] : 0.0; di[p] = p < nb ? dv[p] : 0.0; }
-            double *col = a + (size_t)j * M;
-#pragma unroll 2
-            for (int i = lane; i < M; i += 32) {
-                double v = col[i];
-#pragma unroll
-                for (int p = 0; p < 8; p++) {
-                    if (p < nb) {
-                        if (i == k0 + p) v = cj[p] * di[p];
-                        else v = v - (C[p * Mp + i] * cj[p]) * di[p];
-                    }
+            for (int ks = 0; ks < 2; ks++) {
+                if (ks < KS) {
+                    const double af = -C[(4 * ks + gk) * Mp + 8 * ti + gm];
+                    const double bf = D[(4 * ks + gk) * Mp + 8 * tj + gm];
+                    dmma(c0, c1, af, bf);
                 }
-                col[i] = v;
             }
+            const bool diag = ti == tj;
+            if (i < M && j0 < M && (!diag || i >= j0)) { a[(size_t)j0 * M + i] = c0; a[(size_t)i * M + j0] = c0; }
+            if (i < M && j0 + 1 < M && (!diag || i >= j0 + 1)) { a[(size_t)(j0 + 1) * M + i] = c1; a[(size_t)i * M + j0 + 1] = c1; }
         }
+        __syncthreads();
+        // the panel's own columns, and their mirror image: the rows of the panel's pivots
         for (int idx = threadIdx.x; idx < nb * M; idx += T) {
             const int q = idx / M, i = idx - q * M;
-            a[(size_t)(k0 + q) * M + i] = Pn[q * Mp + i];
+            const double v = Pn[q * Mp + i];
+            a[(size_t)(k0 + q) * M + i] = v;
+            a[(size_t)i * M + k0 + q] = v;
         }
     }
     __syncthreads();
