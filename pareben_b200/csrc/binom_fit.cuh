@@ -286,12 +286,10 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                         { double *tp = s.sigma; s.sigma = s.sigma_new; s.sigma_new = tp; }
                         if (need_sq) {   // reads the UPDATED row j1 (the copy precedes the loop, :1166, 1191)
                             const double *sn = s.sigma + j1 * M;
-                            for (int c = threadIdx.x; c < Kc; c += T) {
-                                double z = 0;
-                                for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sn[j], z);
+                            cache_dot(s, M, Kc, sn, [&](int c, double z) {
                                 s.S_in[c] += z * z * kappa;
                                 s.Q_in[c] += mujj * kappa * z;
-                            }
+                            });
                             if (threadIdx.x == 0) b.flops += 2.0 * Kc * (double)M;
                         }
                     } else if (selected == ACT_ADD) {                                 // ActionAdd*, :830-1003
@@ -349,13 +347,11 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                                 s.sigma_new[idx] = val;
                             }
                             if (need_sq) {
-                                for (int c = threadIdx.x; c < Kc; c += T) {
-                                    double z = 0;
-                                    for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], s.u[j], z);
+                                cache_dot(s, M, Kc, s.u, [&](int c, double z) {
                                     const double mci = s.G[(size_t)grow_new * Kc + c] - z;
                                     s.S_in[c] -= mci * mci * s_ii;
                                     s.Q_in[c] -= mu_i * mci;
-                                }
+                                });
                             }
                             __syncthreads();
                             if (threadIdx.x == 0) {
@@ -378,12 +374,10 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                         __syncthreads();
                         for (int i = threadIdx.x; i < M; i += T) s.mu[i] = s.mu[i] - mujj * sj[i] / sjj;
                         if (need_sq) {
-                            for (int c = threadIdx.x; c < Kc; c += T) {
-                                double z = 0;
-                                for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sj[j], z);
+                            cache_dot(s, M, Kc, sj, [&](int c, double z) {
                                 s.S_in[c] += z * z / sjj;
                                 s.Q_in[c] += z * mujj / sjj;
-                            }
+                            });
                             if (threadIdx.x == 0) b.flops += 2.0 * Kc * (double)M;
                         }
                         for (int idx = threadIdx.x; idx < lastj * lastj; idx += T) {

@@ -706,16 +706,52 @@ __device__ inline void quad_forms(const Slab &s, const double *sigma, double *si
     else quad_forms_mma(s, sigma, sigp_global, M, Kc, v, smem, emit);
 }
 
+// z[c] = sum_j G[row j][c] * vec[j], j ascending, for every candidate c (the S/Q corrections of the three actions,
+// MainEff.c:577-587, 1699-1711, 1800-1808).  Two candidates per thread and four cache rows loaded ahead of their
+// FMAs: the loads come from L2 and a plain loop keeps only one or two of them in flight.
+template <class Emit>
+__device__ inline void cache_dot(const Slab &s, int M, int Kc, const double *__restrict__ vec, Emit emit)
+{
+    const int T = blockDim.x;
+    for (int c0 = threadIdx.x; c0 < Kc; c0 += 2 * T) {
+        const int c1 = c0 + T;
+        const bool two = c1 < Kc;
+        const int cb = two ? c1 : c0;
+        double za = 0, zb = 0;
+        int j = 0;
+        for (; j + 4 <= M; j += 4) {
+            double ga[4], gb[4], v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const size_t o = (size_t)s.grow[j + u] * Kc;
+                ga[u] = s.G[o + c0]; gb[u] = s.G[o + cb]; v[u] = vec[j + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { za = fma(ga[u], v[u], za); zb = fma(gb[u], v[u], zb); }
+        }
+        for (; j < M; j++) {
+            const size_t o = (size_t)s.grow[j] * Kc;
+            const double vj = vec[j];
+            za = fma(s.G[o + c0], vj, za); zb = fma(s.G[o + cb], vj, zb);
+        }
+        emit(c0, za);
+        if (two) emit(c1, zb);
+    }
+}
+
 // dot products of active columns with a vector: out[i] = sum_h phi_i[h] * v[h], one warp per i.
 __device__ inline void phi_dot(const double *phi, int N, int M, const double *v, double *out, double scale)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5, LD = phi_ld(N);
-    for (int i = wid; i < M; i += nw) {
-        const double *p = phi + (size_t)i * LD;
-        double z = 0;
-        for (int h = lane; h < N; h += 32) z = fma(p[h], v[h], z);
-        z = warp_sum(z);
-        if (lane == 0) out[i] = z * scale;
+    for (int i = wid; i < M; i += 2 * nw) {                 // two columns per warp: twice the loads in flight, same sums
+        const int i2 = i + nw;
+        const bool two = i2 < M;
+        const double *p = phi + (size_t)i * LD, *q = phi + (size_t)(two ? i2 : i) * LD;
+        double za = 0, zb = 0;
+#pragma unroll 4
+        for (int h = lane; h < N; h += 32) { const double vv = v[h]; za = fma(p[h], vv, za); zb = fma(q[h], vv, zb); }
+        za = warp_sum(za); zb = warp_sum(zb);
+        if (lane == 0) { out[i] = za * scale; if (two) out[i2] = zb * scale; }
     }
     __syncthreads();
 }
@@ -1385,13 +1421,11 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             s.sigma_new[idx] = s.sigma[idx] - kappa * sj[i] * sj[j];
                         }
                         const double beta = g.beta;
-                        for (int c = threadIdx.x; c < Kc; c += T) {
-                            double z = 0;
-                            for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sj[j], z);
+                        cache_dot(s, M, Kc, sj, [&](int c, double z) {
                             const double bz = beta * z;
                             s.S_in[c] += bz * bz * kappa;
                             s.Q_in[c] += beta * mujj * kappa * z;
-                        }
+                        });
                         if (threadIdx.x == 0) g.flops += 2.0 * Kc * (double)M;
                         updated = true;
                     } else if (selected == ACT_ADD) {                              // ActionAdd*, :1585-1723
@@ -1435,13 +1469,11 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                                 s.sigma_new[idx] = val;
                             }
                             const double beta = g.beta;
-                            for (int c = threadIdx.x; c < Kc; c += T) {
-                                double z = 0;
-                                for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], s.u[j], z);
+                            cache_dot(s, M, Kc, s.u, [&](int c, double z) {
                                 const double mci = beta * s.G[(size_t)grow_new * Kc + c] - beta * z;
                                 s.S_in[c] -= mci * mci * s_ii;
                                 s.Q_in[c] -= mu_i * mci;
-                            }
+                            });
                             __syncthreads();
                             if (threadIdx.x == 0) {
                                 s.used[M] = nu + 1;
@@ -1473,13 +1505,11 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             s.sigma_new[idx] = s.sigma[sjx * M + si] - sj[si] / sjj * sj[sjx];
                         }
                         const double beta = g.beta;
-                        for (int c = threadIdx.x; c < Kc; c += T) {
-                            double z = 0;
-                            for (int j = 0; j < M; j++) z = fma(s.G[(size_t)s.grow[j] * Kc + c], sj[j], z);
+                        cache_dot(s, M, Kc, sj, [&](int c, double z) {
                             const double bz = beta * z;
                             s.S_in[c] += bz * bz / sjj;
                             s.Q_in[c] += beta * z * mujj / sjj;
-                        }
+                        });
                         __syncthreads();
                         if (threadIdx.x == 0) {
                             s.alpha[jj] = al_last;
@@ -1513,11 +1543,16 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                 const int M = g.M;
                 double ee = 0;
                 { PHASE(PH_LOGLIK);
-                for (int h = threadIdx.x; h < N; h += T) {
-                    double pm = 0;
-                    for (int j = 0; j < M; j++) pm = fma(s.phi[(size_t)j * LD + h], s.mu[j], pm);
+                for (int h = threadIdx.x; h < N; h += 2 * T) {          // two rows per thread: twice the loads in flight
+                    const int h2 = h + T;
+                    const bool two = h2 < N;
+                    const double *pa = s.phi + h, *pb = s.phi + (two ? h2 : h);
+                    double pm = 0, pm2 = 0;
+#pragma unroll 4
+                    for (int j = 0; j < M; j++) { const double m = s.mu[j]; pm = fma(pa[(size_t)j * LD], m, pm); pm2 = fma(pb[(size_t)j * LD], m, pm2); }
                     const double e = s.t[h] - pm;
                     ee = fma(e, e, ee);
+                    if (two) { const double e2 = s.t[h2] - pm2; ee = fma(e2, e2, ee); }
                 }
                 ee = block_sum(ee, sc);
                 }
