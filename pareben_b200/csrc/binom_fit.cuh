@@ -28,15 +28,25 @@ struct BinomState {
     double flops;
 };
 
+// z = sum_j phi_j[h] mu[j] and z2 = the same for row h2, j ascending: two rows per thread keep twice the loads of the
+// L2-resident PHI in flight (the sums themselves are unchanged).
+__device__ inline void phi_rows_dot(const double *__restrict__ phi, int LD, int M, const double *__restrict__ mu, int h, int h2,
+                                    double &z, double &z2)
+{
+    const double *pa = phi + h, *pb = phi + h2;
+    double a = 0, b = 0;
+#pragma unroll 4
+    for (int j = 0; j < M; j++) { const double m = mu[j]; a = fma(pa[(size_t)j * LD], m, a); b = fma(pb[(size_t)j * LD], m, b); }
+    z = a; z2 = b;
+}
+
 // eta = PHI mu ; y = sigmoid(eta) ; returns the data error (NEmainEff.c:2013-2032)
 __device__ inline double predictor_and_error(const Slab &s, int N, int M, const double *mu, const double *t,
                                              double *eta, double *yv, const Scratch &sc)
 {
     double err = 0;
     const int LD = phi_ld(N);
-    for (int h = threadIdx.x; h < N; h += blockDim.x) {
-        double z = 0;
-        for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * LD + h], mu[j], z);
+    auto row = [&](int h, double z) {
         eta[h] = z;
         const double y = 1 / (1 + exp(-z));
         yv[h] = y;
@@ -44,6 +54,15 @@ __device__ inline double predictor_and_error(const Slab &s, int N, int M, const 
         if (y != 0) e = e - t[h] * log(y);
         if (y != 1) e = e - (1 - t[h]) * log(1 - y);
         err += e;
+    };
+    const int T = blockDim.x;
+    for (int h = threadIdx.x; h < N; h += 2 * T) {
+        const int h2 = h + T;
+        const bool two = h2 < N;
+        double z, z2;
+        phi_rows_dot(s.phi, LD, M, mu, h, two ? h2 : h, z, z2);
+        row(h, z);
+        if (two) row(h2, z2);
     }
     return block_sum(err, sc);
 }
@@ -79,12 +98,15 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
         // gradient g_j = phi_j'e - alpha_j mu_j (one warp per column), then the Hessian PHI'B PHI + diag(0, alpha)
         // as a tiled Gram matrix; column 0 of PHI is the intercept's all-ones column, so H(0, k) = sum w phi_k
         // and H(0, 0) = sum w come out of the same pass (:1887-1919).
-        for (int j = 1 + wid; j < M; j += nw) {
-            const double *ph = s.phi + (size_t)j * LD;
-            double gj = 0;
-            for (int h = lane; h < N; h += 32) gj = fma(ph[h], e[h], gj);
-            gj = warp_sum(gj);
-            if (lane == 0) g[j] = gj - s.alpha[j - 1] * s.mu[j];
+        for (int j = 1 + wid; j < M; j += 2 * nw) {             // two columns per warp: twice the loads in flight
+            const int j2 = j + nw;
+            const bool two = j2 < M;
+            const double *ph = s.phi + (size_t)j * LD, *ph2 = s.phi + (size_t)(two ? j2 : j) * LD;
+            double gj = 0, gj2 = 0;
+#pragma unroll 4
+            for (int h = lane; h < N; h += 32) { const double eh = e[h]; gj = fma(ph[h], eh, gj); gj2 = fma(ph2[h], eh, gj2); }
+            gj = warp_sum(gj); gj2 = warp_sum(gj2);
+            if (lane == 0) { g[j] = gj - s.alpha[j - 1] * s.mu[j]; if (two) g[j2] = gj2 - s.alpha[j2 - 1] * s.mu[j2]; }
         }
         auto put = [&](int j, int k, double z) {
             if (j == k && j > 0) z += s.alpha[k - 1];
@@ -133,13 +155,13 @@ __device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab
     post_mode<EPIS>(s, b, N, t, sc);
     const int M = b.M;
     double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2;
-    for (int h = threadIdx.x; h < N; h += T) {
-        double z = 0;
-        for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * LD + h], s.mu[j], z);
-        eta[h] = z;
-        const double y = 1 / (1 + exp(-z));
-        yv[h] = y;
-        e[h] = t[h] - y;
+    for (int h = threadIdx.x; h < N; h += 2 * T) {
+        const int h2 = h + T;
+        const bool two = h2 < N;
+        double z, z2;
+        phi_rows_dot(s.phi, LD, M, s.mu, h, two ? h2 : h, z, z2);
+        { eta[h] = z; const double y = 1 / (1 + exp(-z)); yv[h] = y; e[h] = t[h] - y; }
+        if (two) { eta[h2] = z2; const double y = 1 / (1 + exp(-z2)); yv[h2] = y; e[h2] = t[h2] - y; }
     }
     __syncthreads();
     // One pass over the shared training matrix gives, per candidate c,
@@ -424,11 +446,13 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                 PHASE(PH_LOGLIK);
                 const int M = b.M;
                 double ll = 0;
-                for (int h = threadIdx.x; h < N; h += T) {
-                    double z = 0;
-                    for (int j = 0; j < M; j++) z = fma(s.phi[(size_t)j * LD + h], s.mu[j], z);
-                    const double ez = exp(z);
-                    ll += t[h] * log(ez / (1 + ez)) + (1 - t[h]) * log(1 / (1 + ez));
+                for (int h = threadIdx.x; h < N; h += 2 * T) {
+                    const int h2 = h + T;
+                    const bool two = h2 < N;
+                    double z, z2;
+                    phi_rows_dot(s.phi, LD, M, s.mu, h, two ? h2 : h, z, z2);
+                    { const double ez = exp(z); ll += t[h] * log(ez / (1 + ez)) + (1 - t[h]) * log(1 / (1 + ez)); }
+                    if (two) { const double ez = exp(z2); ll += t[h2] * log(ez / (1 + ez)) + (1 - t[h2]) * log(1 / (1 + ez)); }
                 }
                 loglik = block_sum(ll, sc);
                 const double dL = fabs((loglik - logl0) / logl0);
