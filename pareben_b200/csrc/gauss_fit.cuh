@@ -888,12 +888,13 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
 // Register-resident variant for M <= 64 and 256 threads: thread (warp w, lane l) owns rows {l, l+32}
 // x columns {w, w+8, ..., w+56} = 16 entries kept in registers across all M pivots; only the pivot
 // column travels through shared memory (2 x 64 doubles, double-buffered), one barrier per pivot.
+template <int NI>                                     // NI = 1: M <= 32, the second row block does not exist
 __device__ inline bool sweep_regs(double *a, int M, double *colbuf /* 128 doubles of shared memory */)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double r[2][8];
+    double r[NI][8];
 #pragma unroll
-    for (int ii = 0; ii < 2; ii++)
+    for (int ii = 0; ii < NI; ii++)
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
             const int i = lane + 32 * ii, j = wid + 8 * jj;
@@ -902,7 +903,8 @@ __device__ inline bool sweep_regs(double *a, int M, double *colbuf /* 128 double
     double *cur = colbuf, *nxt = colbuf + 64;
     __syncthreads();
     if (wid == 0) {                                   // column 0 lives in warp 0 (jj = 0)
-        cur[lane] = r[0][0]; cur[lane + 32] = r[1][0];
+        cur[lane] = r[0][0];
+        if (NI > 1) cur[lane + 32] = r[NI - 1][0];
     }
     __syncthreads();
     bool ok = true;
@@ -910,7 +912,7 @@ __device__ inline bool sweep_regs(double *a, int M, double *colbuf /* 128 double
         const double d = cur[k];
         if (!(d > 0.0)) { ok = false; break; }
         const double dinv = 1.0 / d, ndinv = -dinv;
-        const double ci0 = cur[lane], ci1 = cur[lane + 32];
+        const double ci0 = cur[lane], ci1 = NI > 1 ? cur[lane + 32] : 0.0;
         const int kn = k + 1;
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
@@ -918,7 +920,7 @@ __device__ inline bool sweep_regs(double *a, int M, double *colbuf /* 128 double
             if (j < M) {                                  // warp-uniform: whole columns beyond M are skipped
                 const double cj = cur[j];
 #pragma unroll
-                for (int ii = 0; ii < 2; ii++) {
+                for (int ii = 0; ii < NI; ii++) {
                     const int i = lane + 32 * ii;
                     const double ci = ii == 0 ? ci0 : ci1;
                     double v;
@@ -936,7 +938,7 @@ __device__ inline bool sweep_regs(double *a, int M, double *colbuf /* 128 double
     }
     if (ok) {
 #pragma unroll
-        for (int ii = 0; ii < 2; ii++)
+        for (int ii = 0; ii < NI; ii++)
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
                 const int i = lane + 32 * ii, j = wid + 8 * jj;
@@ -952,7 +954,7 @@ __device__ inline bool spd_inverse_sweep(double *a, int M, double *colk, const S
     const int T = blockDim.x;
     bool ok;
     if (sm && M <= SWEEP_SMEM_M && T == 256) {
-        ok = sweep_regs(a, M, sm);
+        ok = M <= 32 ? sweep_regs<1>(a, M, sm) : sweep_regs<2>(a, M, sm);
     } else {
         ok = sm ? sweep_panel(a, M, sm) : sweep_core(a, M, colk);          // colk: 2*(cap+1) doubles in the slab
         if (ok) for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -a[idx];
@@ -1065,7 +1067,7 @@ __device__ inline void gram_mma(const double *__restrict__ phi, int N, int LD, i
 // an exposed global load per tile).  Register blocks, row splitting and the fixed-order combination
 // of partial sums are as in gram_tiled.   smem: 2 * 32 * 64 + 64 doubles (w tiles).
 constexpr int GP_ROWS = 32;
-constexpr int GRAM_PIPE_DOUBLES = 2 * GP_ROWS * PHIT_LD + 2 * GP_ROWS;
+constexpr int GRAM_PIPE_DOUBLES = 2 * GP_ROWS * PHIT_LD + 4 * GP_ROWS;
 
 template <class Out>
 __device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, const double *__restrict__ w,
@@ -1073,24 +1075,26 @@ __device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, 
 {
     PHASE(PH_GRAM);
     const int T = blockDim.x;
+    const int NC = M <= 32 ? 32 : 64, TR = M <= 32 ? 2 * GP_ROWS : GP_ROWS;   // narrow matrices: half the columns, twice the rows per tile (half the barriers)
     double *tiles = sm, *wt = sm + 2 * GP_ROWS * PHIT_LD;
-    const int ntile = (N + GP_ROWS - 1) / GP_ROWS;
+    const int ntile = (N + TR - 1) / TR;
     const int nb = (M + 3) >> 2, nblk = nb * (nb + 1) / 2;
     const int nsplit = max(1, min(min(T, 256) / nblk, 8));
     const int blk = threadIdx.x % nblk, split = threadIdx.x / nblk;
     const bool active = threadIdx.x < nblk * nsplit;
     int bj = 0, bk = blk;
     { int rem = blk; while (rem >= nb - bj) { rem -= nb - bj; bj++; } bk = bj + rem; }
-    const int rps = (GP_ROWS + nsplit - 1) / nsplit;            // rows of a tile per split
+    const int rps = (TR + nsplit - 1) / nsplit;                 // rows of a tile per split
+    const int cpr = NC / 2;                                     // 16-byte pieces per row
     auto stage = [&](int t) {
         if (t < ntile) {
             double *dst = tiles + (t & 1) * (GP_ROWS * PHIT_LD);
-            const int h0 = t * GP_ROWS;
-            for (int idx = threadIdx.x; idx < GP_ROWS * (PHIT_LD / 2); idx += T) {
-                const int hl = idx >> 5, q = idx & 31;          // 32 16-byte pieces per row
-                __pipeline_memcpy_async(dst + hl * PHIT_LD + 2 * q, phit + (size_t)min(h0 + hl, N - 1) * PHIT_LD + 2 * q, 16);
+            const int h0 = t * TR;
+            for (int idx = threadIdx.x; idx < TR * cpr; idx += T) {
+                const int hl = idx / cpr, q = idx - hl * cpr;
+                __pipeline_memcpy_async(dst + hl * NC + 2 * q, phit + (size_t)min(h0 + hl, N - 1) * PHIT_LD + 2 * q, 16);
             }
-            if (threadIdx.x < GP_ROWS) wt[(t & 1) * GP_ROWS + threadIdx.x] = (h0 + (int)threadIdx.x < N) ? (w ? w[h0 + threadIdx.x] : 1.0) : 0.0;
+            if (threadIdx.x < TR) wt[(t & 1) * 2 * GP_ROWS + threadIdx.x] = (h0 + (int)threadIdx.x < N) ? (w ? w[h0 + threadIdx.x] : 1.0) : 0.0;
         }
         __pipeline_commit();
     };
@@ -1106,12 +1110,12 @@ __device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, 
         __syncthreads();                                         // tile t visible; everyone finished tile t-1
         stage(t + 1);
         if (active) {
-            const double *tile = tiles + (t & 1) * (GP_ROWS * PHIT_LD), *wv = wt + (t & 1) * GP_ROWS;
-            const int hb = split * rps, he = min(hb + rps, GP_ROWS);
+            const double *tile = tiles + (t & 1) * (GP_ROWS * PHIT_LD), *wv = wt + (t & 1) * 2 * GP_ROWS;
+            const int hb = split * rps, he = min(hb + rps, TR);
 #pragma unroll 2
             for (int hl = hb; hl < he; hl++) {
-                const double4 a4 = *reinterpret_cast<const double4 *>(tile + hl * PHIT_LD + 4 * bj);
-                const double4 b4 = *reinterpret_cast<const double4 *>(tile + hl * PHIT_LD + 4 * bk);
+                const double4 a4 = *reinterpret_cast<const double4 *>(tile + hl * NC + 4 * bj);
+                const double4 b4 = *reinterpret_cast<const double4 *>(tile + hl * NC + 4 * bk);
                 const double ww = wv[hl];                        // rows past N carry weight 0
                 const double av[4] = {a4.x * ww, a4.y * ww, a4.z * ww, a4.w * ww}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
