@@ -24,28 +24,24 @@ struct GaussState {
 };
 
 // ---- contraction: out(r, c) = sum_h x_c[h] * V_r[h]  for r in [0,R), c in [0,Kc) -------------
-// The right-hand sides are first written to a row-major buffer V[h][r] in global memory (leading
-// dimension ldv; rows and columns zero-padded), then streamed through shared memory with cp.async,
-// double-buffered, so the copy of tile s+1 overlaps the arithmetic of tile s and there is ONE
-// barrier per tile.  Two code paths share that staging:
+// The right-hand sides V_r are columns that already exist in memory (the active columns of PHI, the
+// residual vector); nothing is materialised for a contraction.  Three code paths:
 //
 //  * contract_mma (R > SIMT_R_MAX): FP64 tensor-core path, mma.sync.m8n8k4.f64 (DMMA).  A warp owns
-//    16 candidates (two 8-row A tiles) x up to 64 right-hand sides (eight 8-column B tiles) and
-//    keeps the 16 x 64 accumulator block in registers; per 4 rows it loads two A fragments (one
-//    element of the shared training matrix per lane, int8 or f64, prefetched a group ahead) and
-//    up to eight B fragments (conflict-free 8-byte shared loads) for up to sixteen DMMAs.  A thread-
-//    per-candidate DFMA loop needs one 8-byte shared operand per FMA and is capped at 25 % of the
-//    FP64 peak by the 128 B/clk shared-memory return path; the DMMA form needs 1/8 of that traffic.
-//  * contract_simt (R <= SIMT_R_MAX, the single new column of an add): one candidate per thread,
-//    RCS accumulators in registers.
+//    16 candidates (two 8-row A tiles) x up to 32 right-hand sides (four 8-column B tiles) and keeps the
+//    16 x 32 accumulator block in registers.  A: one 32-bit word of the transposed int8 training matrix
+//    per lane per 16 rows (or four doubles), two groups ahead in a register ring; B: 32-row tiles copied
+//    by cp.async straight from the sources into a 3-stage shared-memory ring, conflict-free 8-byte
+//    fragment loads; one barrier per stage.  A thread-per-candidate DFMA loop needs one 8-byte shared
+//    operand per FMA and is capped at 25 % of the FP64 peak by the 128 B/clk shared-memory return path;
+//    the DMMA form needs 1/8 of that traffic.
+//  * contract_col (R == 1, the new column of an add): a warp per candidate, see below.
+//  * contract_simt (2 <= R <= SIMT_R_MAX): one candidate per thread, RCS accumulators in registers.
 //
-// Summation over rows is in ascending h for every (r, c), with identical arithmetic for every
-// candidate, so exact duplicate columns tie exactly.
-//   colval(r, h)  value of right-hand side r at row h (the caller folds any row weight in)
-//   sq_first      when true, right-hand side 0 is contracted with x^2 instead of x
-//                 (the binomial sum_h w[h] x^2, NEmainEff.c:1728-1729)
-constexpr int KT = 32;            // rows per shared-memory stage of the contraction (two groups of 16; a larger stage is faster in isolation but
-                                  // its shared memory comes out of the L1 that the latency-bound phases live on)
+// Every (r, c) is summed in an order that depends only on the row index, with identical arithmetic for
+// every candidate, so exact duplicate columns tie exactly.
+constexpr int KT = 32;            // rows per shared-memory stage of the contraction (two groups of 16; 64 is faster in isolation,
+                                  // but its shared memory comes out of the L1 that the latency-bound phases live on)
 constexpr int QT = 32;            // rows per stage of the row-major tiles (quadratic forms)
 constexpr int NT_MAX = 4;         // 8-column B tiles per pass (32 right-hand sides): 16 x 32 accumulators = 32 registers, no spills
 constexpr int MT = 2;             // 8-candidate A tiles per warp
@@ -68,10 +64,9 @@ __device__ inline void dmma(double &d0, double &d1, double a, double b)
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// KT rows x ncol doubles (ncol a multiple of 2) of V -> dst (leading dimension ldd), 16 bytes per cp.async.
-// PERM: within every group of 16 rows, row 4a + b is stored at position 4b + a, so that the lane that owns
-// four CONSECUTIVE rows of the A operand (one 32-bit load of the transposed int8 matrix) finds the matching
-// B rows at the positions the m8n8k4 fragment layout expects.
+// QT rows x ncol doubles (ncol a multiple of 2) of a row-major matrix V -> dst (leading dimension ldd), 16 bytes per
+// cp.async (the SIGMA tiles of the DMMA quadratic forms).  PERM stores the rows of every group of 16 permuted
+// (row 4a + b at position 4b + a); unused at present.
 template <bool PERM>
 __device__ inline void stage_tile(double *dst, int ldd, const double *__restrict__ V, int ldv, int h0, int r0, int ncol)
 {
