@@ -1170,8 +1170,12 @@ __device__ inline double block_var(const double *t, int N, const Scratch &sc)
 
 __device__ inline void posterior_mean(Slab &s, GaussState &g, int N)
 {   // Mu = beta * SIGMA * PHI' t   (MainEff.c:1256-1280)
-    phi_dot(s.phi, N, g.M, s.t, s.tmp, 1.0);
+    // PHI' t needs no pass over PHI: column j of PHI is candidate used[j]'s normalised column, and x_c' t / s_c is
+    // xt[c], computed for every candidate by the contraction at the top of the outer iteration (t has not changed since).
     const int M = g.M;
+    (void)N;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) s.tmp[j] = s.xt[s.used[j] - 1];
+    __syncthreads();
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         double z = 0;
         for (int j = 0; j < M; j++) z = fma(s.sigma[j * M + i], s.tmp[j], z);
@@ -1445,7 +1449,11 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             contract_x<EPIS>(F, K, Kc, 1, 0,
                                 [&](int) -> const double * { return s.phinew; },
                                 [&](int, bool &dv) -> double * { dv = true; return s.G + (size_t)grow_new * Kc; }, sV);
-                            phi_dot(s.phi, N, M, s.phinew, s.tmp, g.beta);             // tmp = beta PHI' phi
+                            // tmp = beta PHI' phi_new: the entries are already in the cache row just computed
+                            // (G[new][c] = x_c' phi_new / s_c), at the active candidates
+                            __syncthreads();
+                            for (int j = threadIdx.x; j < M; j += T) s.tmp[j] = g.beta * s.G[(size_t)grow_new * Kc + s.used[j] - 1];
+                            __syncthreads();
                             for (int i = threadIdx.x; i < M; i += T) {
                                 double z = 0;
                                 for (int j = 0; j < M; j++) z = fma(s.sigma[i * M + j], s.tmp[j], z);
