@@ -65,6 +65,7 @@ struct FitOutputs {
 // Per-block slab carved out of one big allocation.
 struct Slab {
     double *sigma, *sigma_new, *H;      // cap*cap each
+    double *ptp;                        // cap*cap (leading dimension cap): PHI'PHI of the Gaussian fit, maintained incrementally
     double *phi;                        // phi_ld(nmax) * cap, column-major (column j at phi + j*phi_ld(N), pad rows zero)
     double *phit;                       // (nmax + 32) * PHIT_LD: row-major copy of the first PHIT_LD active columns (binomial IRLS)
     double *G;                          // cap * Kc: physical rows, row r at G + r*Kc
@@ -87,7 +88,7 @@ constexpr int PHIT_LD = 64;       // row-major copy of the first 64 active colum
 
 __host__ __device__ inline size_t slab_doubles(int cap, int nmax, int Kc)
 {
-    return 3 * sig_elems(cap) + (size_t)phi_ld(nmax) * cap + (size_t)(nmax + 32) * PHIT_LD + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
+    return 3 * sig_elems(cap) + (((size_t)cap * cap + 3) & ~(size_t)3) + (size_t)phi_ld(nmax) * cap + (size_t)(nmax + 32) * PHIT_LD + (size_t)cap * Kc + (size_t)7 * Kc + (size_t)5 * nmax +
            (size_t)7 * (cap + 1);
 }
 __host__ __device__ inline size_t slab_ints(int cap, int Kc) { return (size_t)2 * cap + (size_t)5 * Kc; }
@@ -104,6 +105,7 @@ __device__ inline Slab carve_slab(char *base, int cap, int nmax, int Kc)
     s.sigma = d; d += sig_elems(cap);
     s.sigma_new = d; d += sig_elems(cap);
     s.H = d; d += sig_elems(cap);
+    s.ptp = d; d += ((size_t)cap * cap + 3) & ~(size_t)3;          // keeps the arrays behind it 32-byte aligned
     s.phit = d; d += (size_t)(nmax + 32) * PHIT_LD;
     s.phi = d; d += (size_t)phi_ld(nmax) * cap;
     s.G = d; d += (size_t)cap * Kc;

@@ -17,7 +17,7 @@
 namespace pareben {
 
 struct GaussState {
-    int M, n_unused;
+    int M, n_unused, cap;
     double beta;
     int status;
     double flops;
@@ -1191,7 +1191,7 @@ __device__ inline void full_stat(Slab &s, GaussState &g, int N, int Kc, bool fir
         double h = 0;
         for (int k = threadIdx.x; k < N; k += blockDim.x) h = fma(s.phi[k], s.phi[k], h);
         h = block_sum(h, sc);
-        if (threadIdx.x == 0) { s.H[0] = h * g.beta + s.alpha[0]; s.sigma[0] = 1.0 / s.H[0]; }
+        if (threadIdx.x == 0) { s.ptp[0] = h; s.H[0] = h * g.beta + s.alpha[0]; s.sigma[0] = 1.0 / s.H[0]; }
         __syncthreads();
     }
     posterior_mean(s, g, N);
@@ -1208,14 +1208,18 @@ __device__ inline void full_stat(Slab &s, GaussState &g, int N, int Kc, bool fir
 
 __device__ inline bool final_update(Slab &s, GaussState &g, int N, const Scratch &sc)
 {   // FinalUpdate*: H = beta PHI'PHI + diag(alpha), SIGMA = H^-1, Mu  (MainEff.c:1841-1921)
-    const int M = g.M;
+    // PHI'PHI is not recomputed (the reference's dgemm, :1869-1874): it is kept up to date by the add and delete
+    // actions -- a new column's products with the active columns are entries of the cache row the add has just
+    // computed (G[new][c] = x_c' phi_new / s_c) -- so this is an M x M pass, not N x M x M.
+    const int M = g.M, cap = g.cap;
     const double beta = g.beta;
-    gram_mma(s.phi, N, phi_ld(N), M, nullptr, sc.sweep, [&](int i, int j, double z) {
-        double v = z * beta;
-        if (i == j) v += s.alpha[i];
-        s.H[j * M + i] = v; s.H[i * M + j] = v;
-    });
-    for (int idx = threadIdx.x; idx < M * M; idx += blockDim.x) s.sigma[idx] = s.H[idx];
+    (void)N;
+    for (int j = threadIdx.x >> 5; j < M; j += blockDim.x >> 5)
+        for (int i = threadIdx.x & 31; i < M; i += 32) {
+            double v = s.ptp[(size_t)j * cap + i] * beta;
+            if (i == j) v += s.alpha[i];
+            s.H[j * M + i] = v; s.sigma[j * M + i] = v;
+        }
     __syncthreads();
     const bool ok = spd_inverse_sweep(s.sigma, M, s.colk, sc, sc.sweep);
     posterior_mean(s, g, N);
@@ -1310,7 +1314,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
 {
     const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x, LD = phi_ld(N);
     const double *X = F.Xtr, *y = F.ytr, *scale = F.scale;
-    GaussState g; g.M = 1; g.n_unused = 0; g.beta = 0; g.status = 0; g.flops = 0;
+    GaussState g; g.M = 1; g.n_unused = 0; g.cap = cap; g.beta = 0; g.status = 0; g.flops = 0;
 
     for (int j = threadIdx.x; j < cap; j += T) { s.grow[j] = j; s.alpha[j] = 0; s.mu[j] = 0; }
     double b = 0;
@@ -1452,7 +1456,12 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             // tmp = beta PHI' phi_new: the entries are already in the cache row just computed
                             // (G[new][c] = x_c' phi_new / s_c), at the active candidates
                             __syncthreads();
-                            for (int j = threadIdx.x; j < M; j += T) s.tmp[j] = g.beta * s.G[(size_t)grow_new * Kc + s.used[j] - 1];
+                            for (int j = threadIdx.x; j < M; j += T) {
+                                const double pj = s.G[(size_t)grow_new * Kc + s.used[j] - 1];      // phi_j' phi_new
+                                s.tmp[j] = g.beta * pj;
+                                s.ptp[(size_t)j * cap + M] = pj; s.ptp[(size_t)M * cap + j] = pj;
+                            }
+                            if (threadIdx.x == 0) s.ptp[(size_t)M * cap + M] = s.G[(size_t)grow_new * Kc + nu];
                             __syncthreads();
                             for (int i = threadIdx.x; i < M; i += T) {
                                 double z = 0;
@@ -1505,6 +1514,12 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             s.mu[i] = m;
                         }
                         for (int h = threadIdx.x; h < N; h += T) s.phi[(size_t)jj * LD + h] = s.phi[(size_t)lastj * LD + h];
+                        if (jj != lastj) {                                         // PHI'PHI: last row/column into slot jj
+                            for (int i = threadIdx.x; i < lastj; i += T) {
+                                if (i == jj) s.ptp[(size_t)jj * cap + jj] = s.ptp[(size_t)lastj * cap + lastj];
+                                else { s.ptp[(size_t)i * cap + jj] = s.ptp[(size_t)i * cap + lastj]; s.ptp[(size_t)jj * cap + i] = s.ptp[(size_t)lastj * cap + i]; }
+                            }
+                        }
                         // Schur downdate, then move the last row/column into slot jj (:1754-1776)
                         for (int idx = threadIdx.x; idx < lastj * lastj; idx += T) {
                             const int j = idx / lastj, i = idx - j * lastj;
