@@ -186,6 +186,7 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                           double alpha_en, const FitTask &task, const FitOutputs &out, double *sV, const Scratch &sc)
 {
     const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x, LD = phi_ld(N);   // cap counts the intercept slot
+    const int lane_ = threadIdx.x & 31, wid_ = threadIdx.x >> 5, nw_ = T >> 5;
     const double *X = F.Xtr, *t = F.ytr, *scale = F.scale;
     BinomState b; b.M = 2; b.n_unused = 0; b.status = 0; b.flops = 0;
     for (int j = threadIdx.x; j < cap + 1; j += T) { if (j < cap) s.grow[j] = j; s.alpha[j] = 0; s.mu[j] = 0; }
@@ -300,10 +301,11 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                         __syncthreads();
                         if (threadIdx.x == 0) s.alpha[jj] = new_alpha;
                         for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mujj * kappa * sj[i];
-                        for (int idx = threadIdx.x; idx < M * M; idx += T) {
-                            const int j = idx / M, i = idx - j * M;
-                            s.sigma_new[idx] = s.sigma[idx] - kappa * sj[i] * sj[j];
-                        }
+                        for (int j = wid_; j < M; j += nw_)                      // warps own columns, lanes rows: no integer division
+                            for (int i = lane_; i < M; i += 32) {
+                                const int idx = j * M + i;
+                                s.sigma_new[idx] = s.sigma[idx] - kappa * sj[i] * sj[j];
+                            }
                         __syncthreads();
                         { double *tp = s.sigma; s.sigma = s.sigma_new; s.sigma_new = tp; }
                         if (need_sq) {   // reads the UPDATED row j1 (the copy precedes the loop, :1166, 1191)
@@ -360,14 +362,14 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                             if (threadIdx.x == 0) { s.alpha[n_used] = new_alpha; s.mu[M] = mu_i; }
                             for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mu_i * s.u[i];
                             const int M1 = M + 1;
-                            for (int idx = threadIdx.x; idx < M1 * M1; idx += T) {
-                                const int j = idx / M1, i = idx - j * M1;
-                                double val;
-                                if (i < M && j < M) val = s.sigma[j * M + i] + (s_ii * s.u[i]) * s.u[j];
-                                else if (i == M && j == M) val = s_ii;
-                                else val = -s_ii * s.u[i < M ? i : j];
-                                s.sigma_new[idx] = val;
-                            }
+                            for (int j = wid_; j < M1; j += nw_)
+                                for (int i = lane_; i < M1; i += 32) {
+                                    double val;
+                                    if (i < M && j < M) val = s.sigma[j * M + i] + (s_ii * s.u[i]) * s.u[j];
+                                    else if (i == M && j == M) val = s_ii;
+                                    else val = -s_ii * s.u[i < M ? i : j];
+                                    s.sigma_new[j * M1 + i] = val;
+                                }
                             if (need_sq) {
                                 cache_dot(s, M, Kc, s.u, [&](int c, double z) {
                                     const double mci = s.G[(size_t)grow_new * Kc + c] - z;
@@ -402,11 +404,13 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
                             });
                             if (threadIdx.x == 0) b.flops += 2.0 * Kc * (double)M;
                         }
-                        for (int idx = threadIdx.x; idx < lastj * lastj; idx += T) {
-                            const int j = idx / lastj, i = idx - j * lastj;
-                            const int si = (i == j1) ? lastj : i, sjx = (j == j1) ? lastj : j;
-                            s.sigma_new[idx] = EPIS ? s.sigma[sjx * M + si] - sj[si] / sjj * sj[sjx]      // NeFull.c:1612
-                                                    : s.sigma[sjx * M + si] - sj[si] * sj[sjx] / sjj;     // NEmainEff.c:1069
+                        for (int j = wid_; j < lastj; j += nw_) {
+                            const int sjx = (j == j1) ? lastj : j;
+                            for (int i = lane_; i < lastj; i += 32) {
+                                const int si = (i == j1) ? lastj : i;
+                                s.sigma_new[j * lastj + i] = EPIS ? s.sigma[sjx * M + si] - sj[si] / sjj * sj[sjx]      // NeFull.c:1612
+                                                                  : s.sigma[sjx * M + si] - sj[si] * sj[sjx] / sjj;     // NEmainEff.c:1069
+                            }
                         }
                         for (int h = threadIdx.x; h < N; h += T) {
                             if (j1 != lastj) {

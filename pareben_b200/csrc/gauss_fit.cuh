@@ -1313,6 +1313,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                           const Scratch &sc)
 {
     const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x, LD = phi_ld(N);
+    const int lane_ = threadIdx.x & 31, wid_ = threadIdx.x >> 5, nw_ = T >> 5;
     const double *X = F.Xtr, *y = F.ytr, *scale = F.scale;
     GaussState g; g.M = 1; g.n_unused = 0; g.cap = cap; g.beta = 0; g.status = 0; g.flops = 0;
 
@@ -1423,10 +1424,11 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                         __syncthreads();
                         if (threadIdx.x == 0) s.alpha[jj] = new_alpha;
                         for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mujj * kappa * sj[i];
-                        for (int idx = threadIdx.x; idx < M * M; idx += T) {
-                            const int j = idx / M, i = idx - j * M;
-                            s.sigma_new[idx] = s.sigma[idx] - kappa * sj[i] * sj[j];
-                        }
+                        for (int j = wid_; j < M; j += nw_)                      // warps own columns, lanes rows: no integer division
+                            for (int i = lane_; i < M; i += 32) {
+                                const int idx = j * M + i;
+                                s.sigma_new[idx] = s.sigma[idx] - kappa * sj[i] * sj[j];
+                            }
                         const double beta = g.beta;
                         cache_dot(s, M, Kc, sj, [&](int c, double z) {
                             const double bz = beta * z;
@@ -1476,14 +1478,14 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mu_i * s.u[i];
                             if (threadIdx.x == 0) s.mu[M] = mu_i;
                             const int M1 = M + 1;
-                            for (int idx = threadIdx.x; idx < M1 * M1; idx += T) {
-                                const int j = idx / M1, i = idx - j * M1;
-                                double val;
-                                if (i < M && j < M) val = s.sigma[j * M + i] + (s_ii * s.u[i]) * s.u[j];
-                                else if (i == M && j == M) val = s_ii;
-                                else val = -s_ii * s.u[i < M ? i : j];
-                                s.sigma_new[idx] = val;
-                            }
+                            for (int j = wid_; j < M1; j += nw_)
+                                for (int i = lane_; i < M1; i += 32) {
+                                    double val;
+                                    if (i < M && j < M) val = s.sigma[j * M + i] + (s_ii * s.u[i]) * s.u[j];
+                                    else if (i == M && j == M) val = s_ii;
+                                    else val = -s_ii * s.u[i < M ? i : j];
+                                    s.sigma_new[j * M1 + i] = val;
+                                }
                             const double beta = g.beta;
                             cache_dot(s, M, Kc, s.u, [&](int c, double z) {
                                 const double mci = beta * s.G[(size_t)grow_new * Kc + c] - beta * z;
@@ -1521,10 +1523,14 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             }
                         }
                         // Schur downdate, then move the last row/column into slot jj (:1754-1776)
-                        for (int idx = threadIdx.x; idx < lastj * lastj; idx += T) {
-                            const int j = idx / lastj, i = idx - j * lastj;
-                            const int si = (i == jj) ? lastj : i, sjx = (j == jj) ? lastj : j;
-                            s.sigma_new[idx] = s.sigma[sjx * M + si] - sj[si] / sjj * sj[sjx];
+                        for (int i = threadIdx.x; i < M; i += T) s.colk[i] = sj[i] / sjj;      // one division per row, not per entry
+                        __syncthreads();
+                        for (int j = wid_; j < lastj; j += nw_) {
+                            const int sjx = (j == jj) ? lastj : j;
+                            for (int i = lane_; i < lastj; i += 32) {
+                                const int si = (i == jj) ? lastj : i;
+                                s.sigma_new[j * lastj + i] = s.sigma[sjx * M + si] - s.colk[si] * sj[sjx];
+                            }
                         }
                         const double beta = g.beta;
                         cache_dot(s, M, Kc, sj, [&](int c, double z) {
