@@ -833,15 +833,17 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
             const double dinv = 1.0 / d;
             if (threadIdx.x == 0) dv[p] = dinv;
             for (int i = threadIdx.x; i < M; i += T) D[p * Mp + i] = cp[i] * dinv;
-            for (int idx = threadIdx.x; idx < nb * M; idx += T) {
-                const int q = idx / M, i = idx - q * M, j = k0 + q;
+            for (int q = wid; q < nb; q += nw) {              // a warp per panel column, lanes over rows (no integer division)
+                const int j = k0 + q;
                 const double cj = cp[j];
-                double v;
-                if (i == k && j == k) v = -dinv;
-                else if (i == k) v = cj * dinv;
-                else if (j == k) v = cp[i] * dinv;
-                else v = Pn[q * Mp + i] - (cp[i] * cj) * dinv;
-                Pn[q * Mp + i] = v;
+                for (int i = lane; i < M; i += 32) {
+                    double v;
+                    if (i == k && j == k) v = -dinv;
+                    else if (i == k) v = cj * dinv;
+                    else if (j == k) v = cp[i] * dinv;
+                    else v = Pn[q * Mp + i] - (cp[i] * cj) * dinv;
+                    Pn[q * Mp + i] = v;
+                }
             }
         }
         if (!ok) break;
