@@ -448,15 +448,13 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
             if (i_iter == it_max) selected = ACT_TERM;
             {   // global log-likelihood and its relative change (:782-801)
                 PHASE(PH_LOGLIK);
-                const int M = b.M;
+                // the linear predictor PHI mu is already in memory: FullStat left it in w2 after the posterior mode, and
+                // mu has not changed since (every block of actions ends with a FullStat)
+                const double *eta = s.w2;
                 double ll = 0;
-                for (int h = threadIdx.x; h < N; h += 2 * T) {
-                    const int h2 = h + T;
-                    const bool two = h2 < N;
-                    double z, z2;
-                    phi_rows_dot(s.phi, LD, M, s.mu, h, two ? h2 : h, z, z2);
-                    { const double ez = exp(z); ll += t[h] * log(ez / (1 + ez)) + (1 - t[h]) * log(1 / (1 + ez)); }
-                    if (two) { const double ez = exp(z2); ll += t[h2] * log(ez / (1 + ez)) + (1 - t[h2]) * log(1 / (1 + ez)); }
+                for (int h = threadIdx.x; h < N; h += T) {
+                    const double ez = exp(eta[h]);
+                    ll += t[h] * log(ez / (1 + ez)) + (1 - t[h]) * log(1 / (1 + ez));
                 }
                 loglik = block_sum(ll, sc);
                 const double dL = fabs((loglik - logl0) / logl0);
