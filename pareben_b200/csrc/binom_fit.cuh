@@ -67,14 +67,16 @@ __device__ inline double predictor_and_error(const Slab &s, int N, int M, const 
     return block_sum(err, sc);
 }
 
+// Returns true when eta / yv in memory belong to the final mu (the last evaluation was an accepted one).
 template <bool EPIS>
-__device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t, const Scratch &sc)
+__device__ inline bool post_mode(Slab &s, BinomState &b, int N, const double *t, const Scratch &sc)
 {   // fEBCatPostMode*: Newton steps with step halving (NEmainEff.c:1808-2010, NeFull.c:998-1152)
     PHASE(PH_IRLS_OTHER);      // includes the nested Gram/sweep phases (subtract them when reading the counters)
     const int M = b.M, T = blockDim.x, LD = phi_ld(N);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
     double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2, *g = s.gamma, *dmu = s.u, *mun = s.tmp;
     double derr = predictor_and_error(s, N, M, s.mu, t, eta, yv, sc);
+    bool current = true;
     double reg = 0;
     for (int i = 1; i < M; i++) reg = reg + s.alpha[i - 1] * s.mu[i] * s.mu[i] / 2;
     double total = reg + derr;
@@ -131,6 +133,7 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
             for (int j = threadIdx.x; j < M; j += T) mun[j] = s.mu[j] + step * dmu[j];
             __syncthreads();
             derr = predictor_and_error(s, N, M, mun, t, eta, yv, sc);
+            current = false;
             reg = 0;
             for (int j = 1; j < M; j++) reg = reg + s.alpha[j - 1] * mun[j] * mun[j] / 2;
             total = derr + reg;
@@ -139,11 +142,12 @@ __device__ inline void post_mode(Slab &s, BinomState &b, int N, const double *t,
                 __syncthreads();
                 for (int j = threadIdx.x; j < M; j += T) s.mu[j] = mun[j];
                 step = 0;
+                current = true;
             }
             __syncthreads();
         }
     }
-    if (threadIdx.x == 0) b.flops += 0;   // IRLS work is not counted in the score-pass model
+    return current;                        // (IRLS work is not counted in the score-pass model)
 }
 
 template <bool EPIS>
@@ -152,9 +156,14 @@ __device__ inline void binom_full_stat(const Problem &P, const FoldData &F, Slab
 {   // fEBCatFullStat* (NEmainEff.c:1633-1803, NeFull.c:848-993)
     const int N = F.ntr, K = P.K, Kc = P.Kc, T = blockDim.x, LD = phi_ld(N);
     const double *t = F.ytr, *scale = F.scale;
-    post_mode<EPIS>(s, b, N, t, sc);
+    const bool current = post_mode<EPIS>(s, b, N, t, sc);
     const int M = b.M;
     double *yv = s.t, *e = s.e, *w = s.w1, *eta = s.w2;
+    if (!EPIS && current) {
+        // the posterior mode's last evaluation was at the final mu: predictor and probabilities are already in memory
+        // (the Epis variant clamps the stored probabilities in place, NeFull.c:1049-1050, so it recomputes)
+        for (int h = threadIdx.x; h < N; h += T) e[h] = t[h] - yv[h];
+    } else
     for (int h = threadIdx.x; h < N; h += 2 * T) {
         const int h2 = h + T;
         const bool two = h2 < N;
