@@ -100,6 +100,8 @@ __device__ inline bool post_mode(Slab &s, BinomState &b, int N, const double *t,
         // gradient g_j = phi_j'e - alpha_j mu_j (one warp per column), then the Hessian PHI'B PHI + diag(0, alpha)
         // as a tiled Gram matrix; column 0 of PHI is the intercept's all-ones column, so H(0, k) = sum w phi_k
         // and H(0, 0) = sum w come out of the same pass (:1887-1919).
+        const bool fused = M <= PHIT_LD && blockDim.x == 256;     // the Gram pass below also produces PHI'e
+        if (!fused)
         for (int j = 1 + wid; j < M; j += 2 * nw) {             // two columns per warp: twice the loads in flight
             const int j2 = j + nw;
             const bool two = j2 < M;
@@ -114,7 +116,7 @@ __device__ inline bool post_mode(Slab &s, BinomState &b, int N, const double *t,
             if (j == k && j > 0) z += s.alpha[k - 1];
             s.H[k * M + j] = z; s.H[j * M + k] = z;
         };
-        if (M <= PHIT_LD && blockDim.x == 256) gram_pipe(s.phit, N, M, w, sc.sweep, put);   // row-major copy, pipelined
+        if (fused) gram_pipe(s.phit, N, M, w, sc.sweep, put, e, [&](int j, double z) { if (j >= 1) g[j] = z - s.alpha[j - 1] * s.mu[j]; });   // row-major copy, pipelined
         else gram_mma(s.phi, N, LD, M, w, sc.sweep, put);
         for (int idx = threadIdx.x; idx < M * M; idx += T) s.sigma[idx] = s.H[idx];
         __syncthreads();

@@ -1064,16 +1064,18 @@ __device__ inline void gram_mma(const double *__restrict__ phi, int N, int LD, i
 // an exposed global load per tile).  Register blocks, row splitting and the fixed-order combination
 // of partial sums are as in gram_tiled.   smem: 2 * 32 * 64 + 64 doubles (w tiles).
 constexpr int GP_ROWS = 32;
-constexpr int GRAM_PIPE_DOUBLES = 2 * GP_ROWS * PHIT_LD + 4 * GP_ROWS;
+constexpr int GRAM_PIPE_DOUBLES = 2 * GP_ROWS * PHIT_LD + 8 * GP_ROWS;
 
-template <class Out>
+//   ev / outg (optional): the same pass also yields PHI' ev -- the IRLS gradient's data term -- column by column
+//   (accumulated by the threads that own the diagonal blocks), saving a separate pass over PHI.
+template <class Out, class OutG>
 __device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, const double *__restrict__ w,
-                                 double *sm, Out out)
+                                 double *sm, Out out, const double *__restrict__ ev, OutG outg)
 {
     PHASE(PH_GRAM);
     const int T = blockDim.x;
     const int NC = M <= 32 ? 32 : 64, TR = M <= 32 ? 2 * GP_ROWS : GP_ROWS;   // narrow matrices: half the columns, twice the rows per tile (half the barriers)
-    double *tiles = sm, *wt = sm + 2 * GP_ROWS * PHIT_LD;
+    double *tiles = sm, *wt = sm + 2 * GP_ROWS * PHIT_LD, *et = wt + 4 * GP_ROWS;
     const int ntile = (N + TR - 1) / TR;
     const int nb = (M + 3) >> 2, nblk = nb * (nb + 1) / 2;
     const int nsplit = max(1, min(min(T, 256) / nblk, 8));
@@ -1091,10 +1093,16 @@ __device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, 
                 const int hl = idx / cpr, q = idx - hl * cpr;
                 __pipeline_memcpy_async(dst + hl * NC + 2 * q, phit + (size_t)min(h0 + hl, N - 1) * PHIT_LD + 2 * q, 16);
             }
-            if (threadIdx.x < TR) wt[(t & 1) * 2 * GP_ROWS + threadIdx.x] = (h0 + (int)threadIdx.x < N) ? (w ? w[h0 + threadIdx.x] : 1.0) : 0.0;
+            if (threadIdx.x < TR) {
+                const int h = h0 + (int)threadIdx.x;
+                wt[(t & 1) * 2 * GP_ROWS + threadIdx.x] = h < N ? (w ? w[h] : 1.0) : 0.0;
+                if (ev) et[(t & 1) * 2 * GP_ROWS + threadIdx.x] = h < N ? ev[h] : 0.0;
+            }
         }
         __pipeline_commit();
     };
+    const bool grad = ev != nullptr && bj == bk;
+    double ge[4] = {0.0, 0.0, 0.0, 0.0};
     double acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -1119,6 +1127,10 @@ __device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, 
                 for (int a = 0; a < 4; a++)
 #pragma unroll
                     for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+                if (grad) {
+                    const double eh = et[(t & 1) * 2 * GP_ROWS + hl];
+                    ge[0] = fma(a4.x, eh, ge[0]); ge[1] = fma(a4.y, eh, ge[1]); ge[2] = fma(a4.z, eh, ge[2]); ge[3] = fma(a4.w, eh, ge[3]);
+                }
             }
         }
     }
@@ -1142,6 +1154,19 @@ __device__ inline void gram_pipe(const double *__restrict__ phit, int N, int M, 
         if (j < M && k < M && j <= k) out(j, k, z);
     }
     __syncthreads();
+    if (ev) {                                                    // the gradient's partial sums, combined the same way
+        if (active && grad) {
+            double *dst = sm + ((size_t)split * nb + bj) * 4;
+            dst[0] = ge[0]; dst[1] = ge[1]; dst[2] = ge[2]; dst[3] = ge[3];
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nb * 4; idx += T) {
+            double z = 0.0;
+            for (int sp = 0; sp < nsplit; sp++) z += sm[((size_t)sp * nb + (idx >> 2)) * 4 + (idx & 3)];
+            if (idx < M) outg(idx, z);
+        }
+        __syncthreads();
+    }
 }
 
 __device__ inline void refresh_out(const Slab &s, int M, int Kc)
