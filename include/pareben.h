@@ -105,6 +105,17 @@ int pareben_fit(pareben_problem *p, double alpha, double lambda, double *beta_ta
  * full data; epis taken from the problem. */
 int pareben_lambda_max(pareben_problem *p, double *lambda_max);
 
+/* Single-locus prefilter of the published workflow, the step before CrossValidate
+ * (paper_materials/Real Data Analysis/SL_filter.R:17-52): standardise the response and every candidate column with
+ * R's scale() (centre, divide by the n-1 standard deviation) and keep the candidates whose statistic
+ * |ys' xs| / n exceeds a threshold -- tau_main for the k main-effect columns (:21) and, when the problem was created
+ * with epis = 1, tau_pair for the k(k-1)/2 products x_i*x_j, i < j (:28-39).  Candidates are numbered as everywhere
+ * in this library (0..k-1 main effects, then pairs row-major in i < j); the kept ones are written in ascending order
+ * to cand[] / stat[] (each of capacity entries, either may be NULL) and their number to n_kept (which may exceed
+ * capacity: call again with a larger buffer).  Constant columns (sd = 0) are never kept, as in R (NaN > tau is FALSE). */
+int pareben_sl_filter(pareben_problem *p, double tau_main, double tau_pair, int capacity, int *cand, double *stat,
+                      int *n_kept);
+
 /* Work counters of the last pareben_run_fits on this problem, for roofline accounting
  * (SURVEY.md 8d): algorithmic FP64 flops of the contraction/statistics phases, kernel
  * milliseconds measured with CUDA events on the launch stream, launches issued. */

@@ -368,3 +368,33 @@ def local_search_replay(grid_alpha, grid_lambda, fold_err):
         each[ia] = (Alpha[ia], Lambda[idx], sse[idx, 0], sse[idx, 1])
     idx = int(np.argmin(each[:, 2]))
     return each, float(each[idx, 0]), float(each[idx, 1]), mse_cv
+
+
+def sl_filter(BASIS, Target, tau_main: float = 0.02, tau_pair: float = 0.05, epis: bool = True):
+    """SL_filter.R (/root/reference/paper_materials/Real Data Analysis/SL_filter.R:17-52): `scale()` the response and
+    the genotype columns (centre, n-1 standard deviation), keep main effects with |ys' xs| / n > tau_main (:21); for
+    k = 1..K-1 form the products of column k with columns k+1..K, scale them, keep those above tau_pair (:28-39).
+    Returns (main 1-based columns, pairs as 1-based (i, j) with i < j in the script's visiting order, stats)."""
+    X = np.asarray(BASIS, dtype=np.float64)
+    y = np.asarray(Target, dtype=np.float64).ravel()
+    n, k = X.shape
+
+    def scale(a):
+        a = a - a.mean(axis=0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return a / np.sqrt((a * a).sum(axis=0) / (n - 1))
+
+    ys = scale(y[:, None])[:, 0]
+    with np.errstate(invalid="ignore"):
+        sm = np.abs(ys @ scale(X)) / n
+    main = np.nonzero(sm > tau_main)[0]
+    pairs, sp = [], []
+    if epis:
+        for a in range(k - 1):
+            prod = X[:, a + 1:] * X[:, [a]]
+            with np.errstate(invalid="ignore"):
+                st = np.abs(ys @ scale(prod)) / n
+            hit = np.nonzero(st > tau_pair)[0]
+            pairs += [(a + 1, a + 2 + int(b)) for b in hit]
+            sp += [float(st[b]) for b in hit]
+    return main + 1, np.array(pairs, dtype=np.int64).reshape(-1, 2), sm[main], np.array(sp)

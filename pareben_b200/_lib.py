@@ -32,6 +32,7 @@ SIGNATURES = {
     "pareben_shard_plan": (ctypes.c_int, [_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _ip, _ip]),
     "pareben_fit": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, _dp, _dp, _dp, _dp, _ip]),
     "pareben_lambda_max": (ctypes.c_int, [_vp, _dp]),
+    "pareben_sl_filter": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, _ip, _dp, _ip]),
     "pareben_last_counters": (ctypes.c_int, [_vp, _dp, _dp, _ip]),
     "pareben_measure_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _dp]),
     "pareben_device_count": (ctypes.c_int, []),
@@ -139,6 +140,16 @@ class Problem:
         out = np.zeros(1)
         _check(load().pareben_lambda_max(self._h, _d(out)))
         return float(out[0])
+
+    def sl_filter(self, tau_main: float, tau_pair: float):
+        """pareben_sl_filter: (candidate ids ascending, statistics) of the single-locus prefilter."""
+        cap = 1 << 16
+        while True:
+            cand = np.empty(cap, np.int32); stat = np.empty(cap); cnt = ctypes.c_int(0)
+            _check(load().pareben_sl_filter(self._h, float(tau_main), float(tau_pair), cap, _i(cand), _d(stat), ctypes.byref(cnt)))
+            if cnt.value <= cap:
+                return cand[:cnt.value].copy(), stat[:cnt.value].copy()
+            cap = cnt.value
 
     def counters(self):
         fl = np.zeros(1); ms = np.zeros(1); ln = np.zeros(1, np.int32)

@@ -200,3 +200,22 @@ def EBelasticNet_Binomial(BASIS, Target, lam, alpha, Epis="no", verbose=0, devic
     keep = np.nonzero(table[:, 2] != 0)[0]
     return {"weight": _weight_table(table, keep, epis, X.shape[0]), "logLikelihood": logl, "WaldScore": wald,
             "Intercept": icpt.copy(), "lambda": lam, "alpha": alpha, "status": status}
+
+
+def SLFilter(BASIS, Target, tau_main: float = 0.02, tau_pair: float = 0.05, Epis: str = "yes", device: int = 0):
+    """The single-locus prefilter that precedes CrossValidate in the published workflow
+    (paper_materials/Real Data Analysis/SL_filter.R:17-52): standardised-correlation screening of the main-effect
+    columns (> tau_main) and, for Epis="yes", of all pairwise products (> tau_pair), on the device.
+    Returns {"main": 1-based column numbers, "pairs": (n, 2) 1-based locus pairs i < j, "stat_main", "stat_pairs"}."""
+    X = np.asarray(BASIS, dtype=np.float64)
+    k = X.shape[1]
+    with _lib.Problem(X, Target, None, 0, Epis == "yes", "gaussian", device=device) as p:
+        cand, stat = p.sl_filter(tau_main, tau_pair)
+    main = cand < k
+    pc = cand[~main].astype(np.int64) - k
+    # invert c = i*(2k-i-1)/2 + (j-i-1) for i < j (the enumeration of elasticNetLinearNeFull2.c:115-134)
+    i = np.floor(((2 * k - 1) - np.sqrt((2 * k - 1) ** 2 - 8.0 * pc)) / 2).astype(np.int64)
+    i = np.where(i * (2 * k - i - 1) // 2 > pc, i - 1, i)
+    i = np.where((i + 1) * (2 * k - i - 2) // 2 <= pc, i + 1, i)
+    j = pc - i * (2 * k - i - 1) // 2 + i + 1
+    return {"main": cand[main] + 1, "pairs": np.stack([i + 1, j + 1], axis=1), "stat_main": stat[main], "stat_pairs": stat[~main]}

@@ -202,6 +202,24 @@ Variant make_variant(int epis, int prior)
 
 }  // namespace
 
+// single-locus statistic |ys' xs| / n of SL_filter.R:21,37 for candidates [c_begin, c_end): two passes over the rows
+// (mean, then centred sums) like R's scale()
+template <bool EPIS>
+__global__ void sl_stat_kernel(const double *__restrict__ X, int N, int K, int c_begin, int c_end,
+                               const double *__restrict__ ys, double *__restrict__ stat)
+{
+    const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_end) return;
+    Cand<EPIS> cd(c, K);
+    double sx = 0;
+    for (int h = 0; h < N; h++) sx += cd.at(X + (size_t)h * K);
+    const double mean = sx / N;
+    double ss = 0, sy = 0;
+    for (int h = 0; h < N; h++) { const double d = cd.at(X + (size_t)h * K) - mean; ss = fma(d, d, ss); sy = fma(d, ys[h], sy); }
+    const double sd = sqrt(ss / (N - 1));
+    stat[c - c_begin] = fabs(sy / sd) / N;          // sd == 0 -> NaN or Inf*0: never passes the host's `> tau` test
+}
+
 // ---------------------------------------------------------------------------------------------
 struct pareben_problem {
     int device = 0;
@@ -665,10 +683,9 @@ extern "C" int pareben_lambda_max(pareben_problem *p, double *lambda_max)
         for (int i = 0; i < n; i++) { centred[i] = (double)(y[i] - (double)mean); ss += (long double)centred[i] * centred[i]; }
         const double nrm = std::sqrt((double)ss);
         for (int i = 0; i < n; i++) resp[i] = centred[i] / nrm;
-        double *d_rows_x = nullptr, *d_resp = nullptr, *d_max = nullptr; int *d_rows = nullptr;
-        CU(cudaMalloc(&d_rows_x, sizeof(double) * (size_t)n * k));
-        CU(cudaMalloc(&d_resp, sizeof(double) * n));
-        CU(cudaMalloc(&d_rows, sizeof(int) * n));
+        // scratch comes from the problem's pooled allocations (returned to the pool with the problem; nothing to leak on error)
+        double *d_rows_x = p->dalloc<double>((size_t)n * k), *d_resp = p->dalloc<double>(n);
+        int *d_rows = p->dalloc<int>(n);
         std::vector<int> rows(n); for (int i = 0; i < n; i++) rows[i] = i;
         CU(cudaMemcpy(d_rows, rows.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
         gather_rows_kernel<<<dim3((n + 31) / 32, (k + 31) / 32), dim3(32, 8), 0, p->stream>>>(p->d_Xcol, n, k, d_rows, n, d_rows_x);
@@ -677,19 +694,71 @@ extern "C" int pareben_lambda_max(pareben_problem *p, double *lambda_max)
             const int nb = (c1 - c0 + 255) / 256;
             if (nb <= 0) return;
             CU(cudaMemcpyAsync(d_resp, r.data(), sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
-            CU(cudaMalloc(&d_max, sizeof(double) * nb));
+            double *d_max = p->dalloc<double>(nb);
             if (epis) lambda_max_kernel<true><<<nb, 256, 0, p->stream>>>(d_rows_x, n, k, c0, c1, d_resp, d_max);
             else lambda_max_kernel<false><<<nb, 256, 0, p->stream>>>(d_rows_x, n, k, c0, c1, d_resp, d_max);
+            CU(cudaGetLastError());
             std::vector<double> hm(nb);
             CU(cudaMemcpyAsync(hm.data(), d_max, sizeof(double) * nb, cudaMemcpyDeviceToHost, p->stream));
             CU(cudaStreamSynchronize(p->stream));
             for (double v : hm) if (v > best) best = v;
-            cudaFree(d_max); d_max = nullptr;
         };
         pass(0, k, resp, false);                       // main effects against the normalised response (:14-19)
         if (p->epis) pass(k, p->kc, centred, true);    // pairs against the UN-normalised centred response (:24-27)
-        cudaFree(d_rows_x); cudaFree(d_resp); cudaFree(d_rows);
         *lambda_max = best;
+    } catch (std::pair<int, std::string> &e) {
+        return fail(e.first, e.second);
+    }
+    return PAREBEN_OK;
+}
+
+extern "C" int pareben_sl_filter(pareben_problem *p, double tau_main, double tau_pair, int capacity, int *cand, double *stat,
+                                 int *n_kept)
+{
+    if (!p || !n_kept || capacity < 0) return fail(PAREBEN_EINVAL, "pareben_sl_filter: bad argument");
+    try {
+        CU(cudaSetDevice(p->device));
+        const int n = p->n, k = p->k;
+        std::vector<double> y(n), ys(n);
+        CU(cudaMemcpy(y.data(), p->d_y, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        long double s = 0; for (double v : y) s += v;
+        long double mean = s / n, t = 0; for (double v : y) t += (v - mean);
+        mean += t / n;                                                     // R's two-pass mean
+        long double ss = 0; for (double v : y) ss += ((long double)v - mean) * ((long double)v - mean);
+        const double sd = std::sqrt((double)(ss / (n - 1)));
+        for (int i = 0; i < n; i++) ys[i] = (double)(y[i] - (double)mean) / sd;
+        double *d_rows_x = p->dalloc<double>((size_t)n * k), *d_ys = p->dalloc<double>(n);
+        int *d_rows = p->dalloc<int>(n);
+        std::vector<int> rows(n); for (int i = 0; i < n; i++) rows[i] = i;
+        CU(cudaMemcpy(d_rows, rows.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(d_ys, ys.data(), sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
+        gather_rows_kernel<<<dim3((n + 31) / 32, (k + 31) / 32), dim3(32, 8), 0, p->stream>>>(p->d_Xcol, n, k, d_rows, n, d_rows_x);
+        const int chunk = 1 << 22;
+        double *d_stat = p->dalloc<double>(chunk);
+        std::vector<double> h_stat(chunk);
+        long long kept = 0;
+        const int c_total = p->epis ? p->kc : k;
+        for (int c0 = 0; c0 < c_total; ) {
+            // a chunk never straddles the main-effect / pair boundary (different thresholds, different column rule)
+            const bool pairs = c0 >= k;
+            const int c1 = std::min(pairs ? c_total : k, c0 + chunk);
+            const int nb = (c1 - c0 + 255) / 256;
+            if (pairs) sl_stat_kernel<true><<<nb, 256, 0, p->stream>>>(d_rows_x, n, k, c0, c1, d_ys, d_stat);
+            else sl_stat_kernel<false><<<nb, 256, 0, p->stream>>>(d_rows_x, n, k, c0, c1, d_ys, d_stat);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(h_stat.data(), d_stat, sizeof(double) * (c1 - c0), cudaMemcpyDeviceToHost, p->stream));
+            CU(cudaStreamSynchronize(p->stream));
+            const double tau = pairs ? tau_pair : tau_main;
+            for (int c = c0; c < c1; c++) {
+                const double v = h_stat[c - c0];
+                if (v > tau) {
+                    if (kept < capacity) { if (cand) cand[kept] = c; if (stat) stat[kept] = v; }
+                    kept++;
+                }
+            }
+            c0 = c1;
+        }
+        *n_kept = (int)std::min<long long>(kept, 0x7fffffff);
     } catch (std::pair<int, std::string> &e) {
         return fail(e.first, e.second);
     }

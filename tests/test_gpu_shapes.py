@@ -132,3 +132,21 @@ def test_odd_row_counts_and_tiny_folds(pb):
         X = _genotypes(rng, n, k, block=8)
         y = 5 + 1.5 * X[:, 1] - X[:, k // 2] + rng.normal(0, 1.0, n)
         _check(pb, X, y, nf, np.array([0.6, 0.05]), np.array([1.0, 0.25]), False, "gaussian", 1e-8)
+
+
+def test_sl_prefilter_matches_the_r_script(pb, bundled):
+    """the single-locus prefilter that precedes CrossValidate in the published workflow
+    (SL_filter.R), on the device, against the numpy restatement of the script: same kept sets, in the same order,
+    statistics to 1e-12; a constant column is never kept."""
+    X, y = bundled["BASIS"][:, :80].astype(float), bundled["y"]
+    X[:, 7] = 1.0                                   # constant column: sd = 0 -> NaN in R, dropped
+    for tau_m, tau_p, epis in ((0.05, 0.08, "yes"), (0.02, 0.05, "yes"), (0.03, 0.0, "no")):
+        want_m, want_p, sm, sp = R.sl_filter(X, y, tau_m, tau_p, epis == "yes")
+        got = pb.SLFilter(X, y, tau_m, tau_p, epis)
+        assert np.array_equal(got["main"], want_m) and 8 not in got["main"]
+        assert np.allclose(got["stat_main"], sm, rtol=1e-12, atol=0)
+        if epis == "yes":
+            assert np.array_equal(got["pairs"], want_p)
+            assert np.allclose(got["stat_pairs"], sp, rtol=1e-12, atol=0)
+        else:
+            assert got["pairs"].shape[0] == 0

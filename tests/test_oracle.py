@@ -168,3 +168,19 @@ def test_port_binomial_epis_slice(bundled, built):
     assert np.array_equal(ns, g["n_selected"][idx])
     ref = g["fold_err"][idx]
     assert np.max(np.abs(err - ref) / np.maximum(np.abs(ref), 1e-12)) < 1e-9
+
+
+def test_sl_filter_restatement_matches_correlation(bundled):
+    """SL_filter.R's statistic |ys' xs| / n is (n-1)/n times the absolute Pearson correlation: check the numpy restatement
+    against np.corrcoef on the bundled data (main effects and pairs)."""
+    X, y = bundled["BASIS"][:, :30].astype(float), bundled["y"]
+    n = X.shape[0]
+    main, pairs, sm, sp = R.sl_filter(X, y, 0.05, 0.05)
+    assert main.size > 0 and pairs.shape[0] > 0 and np.all(pairs[:, 0] < pairs[:, 1])
+    for c, v in zip(main, sm):
+        assert abs(v - abs(np.corrcoef(X[:, c - 1], y)[0, 1]) * (n - 1) / n) < 1e-12
+    for (i, j), v in list(zip(pairs, sp))[:20]:
+        assert abs(v - abs(np.corrcoef(X[:, i - 1] * X[:, j - 1], y)[0, 1]) * (n - 1) / n) < 1e-12
+    # every candidate not returned is below its threshold
+    allm = np.array([abs(np.corrcoef(X[:, c], y)[0, 1]) * (n - 1) / n for c in range(X.shape[1])])
+    assert set(np.nonzero(allm > 0.05)[0] + 1) == set(main.tolist())
