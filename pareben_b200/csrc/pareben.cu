@@ -223,7 +223,7 @@ __global__ void sl_stat_kernel(const double *__restrict__ X, int N, int K, int c
 // ---------------------------------------------------------------------------------------------
 struct pareben_problem {
     int device = 0;
-    int n = 0, k = 0, kc = 0, n_folds = 0, epis = 0, prior = 0, cap = 0, nmax = 0;
+    int n = 0, k = 0, kc = 0, n_folds = 0, epis = 0, prior = 0, cap = 0, nmax = 0, min_ntr = 0;
     int sm_count = 0;
     std::vector<PoolEntry> allocs;       // every device buffer of this problem (returned to the pool on destroy)
     FoldData *d_folds = nullptr;
@@ -261,6 +261,66 @@ static int reference_basis_max(int n_train, int k, int kc, int epis, int prior)
     if (prior == PAREBEN_BINOMIAL) return epis ? 2 * k : k;                        // bMax (EBelasticNet.Binomial.R:8,30)
     if (!epis) { int b = (int)(1e7 / kc); return b > kc ? kc : b; }                // MainEff.c:68-69
     return n_train > k ? 2 * k : (n_train < 200 ? 4 * k : k);                      // NeFull2.c:67-80
+}
+
+// The per-block work slabs are only needed by the fit kernel: they are sized and allocated at the first
+// pareben_run_fits / pareben_fit of a problem (lambda_max and the single-locus prefilter never touch them, and an
+// Epis problem's candidate cache can be far larger than those two need).  Throws like the CU() macro.
+static void ensure_slabs(pareben_problem *p)
+{
+    if (p->d_slabs) return;
+    // basis cap: the reference's basisMax, bounded so that the per-block slab stays reasonable.
+    int cap = reference_basis_max(p->min_ntr, p->k, p->kc, p->epis, p->prior);
+    const char *env_cap = getenv("PAREBEN_BASIS_CAP");
+    int hard = env_cap ? atoi(env_cap) : 1024;
+    if (hard < 2) hard = 2;
+    if (p->prior == PAREBEN_BINOMIAL) cap += 1;       // slot 0 is the intercept
+    p->cap = std::min(cap, hard);
+    if (p->cap < 2) p->cap = 2;
+
+    // persistent grid: blocks per SM limited by memory for slabs
+    p->slab_stride = slab_bytes(p->cap, p->nmax, p->kc);
+    // resident blocks per SM of the kernel variant this problem will launch (asked once per variant:
+    // the occupancy query, like cudaMemGetInfo below, costs up to tens of milliseconds)
+    int per_sm = 1;
+    {
+        // Block size: measured on B200 (config 2 / bundled Gaussian): 256 threads x 2 blocks per SM beats
+        // 128 x 4 (-5 % / -43 %) and 64 x 8 (-40 % / -70 %) (measured with an earlier build that had a run-time block size).
+        p->threads = FIT_THREADS_HOST;     // gram_tiled() maps 16 x 16 register blocks onto exactly 256 threads
+        static int occ_cache[4] = {0, 0, 0, 0};
+        int &occ = occ_cache[(p->prior == PAREBEN_BINOMIAL ? 2 : 0) + (p->epis ? 1 : 0)];
+        if (!occ) {
+            cudaError_t e;
+            if (p->prior == PAREBEN_GAUSSIAN) e = p->epis ? occupancy_ge(&occ, p->threads) : occupancy_gm(&occ, p->threads);
+            else e = p->epis ? occupancy_be(&occ, p->threads) : occupancy_bm(&occ, p->threads);
+            CU(e);
+        }
+        per_sm = std::max(1, occ);
+    }
+    const char *env_bps = getenv("PAREBEN_BLOCKS_PER_SM");
+    if (env_bps) per_sm = std::max(1, std::min(per_sm, atoi(env_bps)));
+    // First try the pool with the full-occupancy slab (the steady state of repeated CrossValidate calls);
+    // only a miss pays for cudaMemGetInfo and cudaMalloc.
+    p->n_slabs = per_sm * p->sm_count;
+    p->slab_total = (size_t)p->n_slabs * p->slab_stride;
+    {
+        size_t got = 0;
+        void *q = pool_take(p->device, p->slab_total, true, &got);
+        if (q) { p->d_slabs = (char *)q; p->slab_total = got; }
+    }
+    if (!p->d_slabs) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        while (per_sm > 1 && (size_t)per_sm * p->sm_count * p->slab_stride > free_b / 2) per_sm--;
+        p->n_slabs = per_sm * p->sm_count;
+        while (p->n_slabs > 1 && (size_t)p->n_slabs * p->slab_stride > free_b - (free_b >> 3)) p->n_slabs /= 2;   // huge problems: fewer blocks
+        p->slab_total = (size_t)p->n_slabs * p->slab_stride;
+        if (p->slab_total > free_b - (free_b >> 3))
+            throw std::make_pair((int)PAREBEN_ENOMEM, std::string("per-block work slabs do not fit in device memory; lower PAREBEN_BASIS_CAP"));
+        void *q = nullptr;
+        CU(cudaMalloc(&q, p->slab_total));
+        p->d_slabs = (char *)q;
+    }
 }
 
 extern "C" int pareben_device_count(void)
@@ -377,59 +437,7 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         p->d_folds = p->dalloc<FoldData>(nf + 1);
         CU(cudaMemcpyAsync(p->d_folds, p->h_folds.data(), sizeof(FoldData) * (nf + 1), cudaMemcpyHostToDevice, p->stream));
 
-        // basis cap: the reference's basisMax, bounded so that the per-block slab stays reasonable.
-        int cap = reference_basis_max(min_ntr, k, p->kc, epis, prior);
-        const char *env_cap = getenv("PAREBEN_BASIS_CAP");
-        int hard = env_cap ? atoi(env_cap) : 1024;
-        if (hard < 2) hard = 2;
-        if (prior == PAREBEN_BINOMIAL) cap += 1;       // slot 0 is the intercept
-        p->cap = std::min(cap, hard);
-        if (p->cap < 2) p->cap = 2;
-
-        // persistent grid: blocks per SM limited by memory for slabs
-        p->slab_stride = slab_bytes(p->cap, p->nmax, p->kc);
-        // resident blocks per SM of the kernel variant this problem will launch (asked once per variant:
-        // the occupancy query, like cudaMemGetInfo below, costs up to tens of milliseconds)
-        int per_sm = 1;
-        {
-            // Block size: measured on B200 (config 2 / bundled Gaussian): 256 threads x 2 blocks per SM beats
-            // 128 x 4 (-5 % / -43 %) and 64 x 8 (-40 % / -70 %) (measured with an earlier build that had a run-time block size).
-            p->threads = FIT_THREADS_HOST;     // gram_tiled() maps 16 x 16 register blocks onto exactly 256 threads
-            static int occ_cache[4] = {0, 0, 0, 0};
-            int &occ = occ_cache[(prior == PAREBEN_BINOMIAL ? 2 : 0) + (epis ? 1 : 0)];
-            if (!occ) {
-                cudaError_t e;
-                if (prior == PAREBEN_GAUSSIAN) e = epis ? occupancy_ge(&occ, p->threads) : occupancy_gm(&occ, p->threads);
-                else e = epis ? occupancy_be(&occ, p->threads) : occupancy_bm(&occ, p->threads);
-                CU(e);
-            }
-            per_sm = std::max(1, occ);
-        }
-        const char *env_bps = getenv("PAREBEN_BLOCKS_PER_SM");
-        if (env_bps) per_sm = std::max(1, std::min(per_sm, atoi(env_bps)));
-        // First try the pool with the full-occupancy slab (the steady state of repeated CrossValidate calls);
-        // only a miss pays for cudaMemGetInfo and cudaMalloc.
-        p->n_slabs = per_sm * p->sm_count;
-        p->slab_total = (size_t)p->n_slabs * p->slab_stride;
-        {
-            size_t got = 0;
-            void *q = pool_take(device, p->slab_total, true, &got);
-            if (q) { p->d_slabs = (char *)q; p->slab_total = got; }
-        }
-        if (!p->d_slabs) {
-            size_t free_b = 0, total_b = 0;
-            CU(cudaMemGetInfo(&free_b, &total_b));
-            while (per_sm > 1 && (size_t)per_sm * p->sm_count * p->slab_stride > free_b / 2) per_sm--;
-            p->n_slabs = per_sm * p->sm_count;
-            while (p->n_slabs > 1 && (size_t)p->n_slabs * p->slab_stride > free_b - (free_b >> 3)) p->n_slabs /= 2;   // huge problems: fewer blocks
-            p->slab_total = (size_t)p->n_slabs * p->slab_stride;
-            if (p->slab_total > free_b - (free_b >> 3))
-                throw std::make_pair((int)PAREBEN_ENOMEM, std::string("per-block work slabs do not fit in device memory; lower PAREBEN_BASIS_CAP"));
-            void *q = nullptr;
-            CU(cudaMalloc(&q, p->slab_total));
-            p->d_slabs = (char *)q;
-        }
-        lap("cap/occupancy/slab");
+        p->min_ntr = min_ntr;
         p->d_queue = p->dalloc<int>(1);
         p->d_flops = p->dalloc<double>(1);
         CU(cudaStreamSynchronize(p->stream));
@@ -472,6 +480,7 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
     int ns = 0;
     try {
         CU(cudaSetDevice(p->device));
+        ensure_slabs(p);
         std::vector<FitTask> tasks(n_fits);
         for (int i = 0; i < n_fits; i++) {
             if (fold[i] < 0 || fold[i] > p->n_folds || (p->n_folds > 0 && fold[i] == 0) || !p->h_folds[fold[i]].Xtr)
