@@ -154,14 +154,17 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything libraries print while the run is in progress (NCCL writes its
+    # version banner to stdout when the communicator comes up) is sent to stderr instead
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     pb.load()
     if pb.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU implementation; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     X, y, n_folds = load_workload()
@@ -284,6 +287,8 @@ def run_gpu(args):
                              "peak_source": f"on-box probe at bench start: DFMA {peak_dfma:.1f}, DMMA {peak_dmma:.1f} TFLOP/s "
                                             "(MEASURED_PEAKS.json has no FP64 entry)"},
                 "cpu_baseline": cpu, "wall_s_timed_region": wall}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     prob.close()
     if world > 1:
