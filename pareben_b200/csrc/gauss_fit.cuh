@@ -490,13 +490,13 @@ __device__ inline void contract_x(const FoldData &F, int K, int Kc, int R, int n
 // SIGMA is first copied to a padded layout (leading dimension ldp, multiple of 8, in `sigp`) so a
 // thread reads 8 consecutive entries of a row with two 32-byte loads; z_p accumulates over j in
 // ascending order and quad over p in ascending order, as the reference's loops do.
-template <class Emit>
+template <int PW, class Emit>       // PW = z accumulators per candidate: the cache rows are re-read M / PW times
 __device__ inline void quad_forms_simt(const Slab &s, const double *sigma, double *sigp_global, int M, int Kc, const double *v,
                                   double *smem /* >= 4096 + 1040 doubles */, Emit emit)
 {
     PHASE(PH_QUAD);
     const int T = blockDim.x;
-    const int ldp = (M + 7) & ~7;
+    const int ldp = (M + PW - 1) / PW * PW;
     // padded copy sigp[j][p] = SIGMA(p, j): in shared memory when it fits (M <= 64), else in the spare SIGMA buffer
     double *sigp = (M * ldp <= 4096) ? smem : sigp_global;
     size_t *rowoff = reinterpret_cast<size_t *>(smem + 4096);          // G row offsets: no dependent index load in the hot loop
@@ -515,10 +515,10 @@ __device__ inline void quad_forms_simt(const Slab &s, const double *sigma, doubl
         const bool la = ca < Kc, lb = cb < Kc;
         const int xa = la ? ca : 0, xb = lb ? cb : 0;
         double quad_a = 0, lin_a = 0, quad_b = 0, lin_b = 0;
-        for (int p0 = 0; p0 < M; p0 += 8) {
-            double za[8], zb[8];
+        for (int p0 = 0; p0 < M; p0 += PW) {
+            double za[PW], zb[PW];
 #pragma unroll
-            for (int q = 0; q < 8; q++) { za[q] = 0.0; zb[q] = 0.0; }
+            for (int q = 0; q < PW; q++) { za[q] = 0.0; zb[q] = 0.0; }
             for (int j = 0; j < M; j += 4) {
                 double ga[4], gb[4];
 #pragma unroll
@@ -530,16 +530,19 @@ __device__ inline void quad_forms_simt(const Slab &s, const double *sigma, doubl
                 for (int u = 0; u < 4; u++) {
                     if (j + u < M) {
                         const double4 *row = reinterpret_cast<const double4 *>(sigp + (size_t)(j + u) * ldp + p0);
-                        const double4 a = row[0], b = row[1];
-                        za[0] = fma(ga[u], a.x, za[0]); za[1] = fma(ga[u], a.y, za[1]); za[2] = fma(ga[u], a.z, za[2]); za[3] = fma(ga[u], a.w, za[3]);
-                        za[4] = fma(ga[u], b.x, za[4]); za[5] = fma(ga[u], b.y, za[5]); za[6] = fma(ga[u], b.z, za[6]); za[7] = fma(ga[u], b.w, za[7]);
-                        zb[0] = fma(gb[u], a.x, zb[0]); zb[1] = fma(gb[u], a.y, zb[1]); zb[2] = fma(gb[u], a.z, zb[2]); zb[3] = fma(gb[u], a.w, zb[3]);
-                        zb[4] = fma(gb[u], b.x, zb[4]); zb[5] = fma(gb[u], b.y, zb[5]); zb[6] = fma(gb[u], b.z, zb[6]); zb[7] = fma(gb[u], b.w, zb[7]);
+#pragma unroll
+                        for (int q4 = 0; q4 < PW / 4; q4++) {
+                            const double4 a = row[q4];
+                            za[4 * q4 + 0] = fma(ga[u], a.x, za[4 * q4 + 0]); za[4 * q4 + 1] = fma(ga[u], a.y, za[4 * q4 + 1]);
+                            za[4 * q4 + 2] = fma(ga[u], a.z, za[4 * q4 + 2]); za[4 * q4 + 3] = fma(ga[u], a.w, za[4 * q4 + 3]);
+                            zb[4 * q4 + 0] = fma(gb[u], a.x, zb[4 * q4 + 0]); zb[4 * q4 + 1] = fma(gb[u], a.y, zb[4 * q4 + 1]);
+                            zb[4 * q4 + 2] = fma(gb[u], a.z, zb[4 * q4 + 2]); zb[4 * q4 + 3] = fma(gb[u], a.w, zb[4 * q4 + 3]);
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
+            for (int q = 0; q < PW; q++) {
                 if (p0 + q < M) {
                     const size_t o = roff(p0 + q);
                     const double gpa = s.G[o + xa], gpb = s.G[o + xb];
@@ -697,7 +700,7 @@ template <class Emit>
 __device__ inline void quad_forms(const Slab &s, const double *sigma, double *sigp_global, int M, int Kc, const double *v,
                                   double *smem, Emit emit)
 {
-    if (M <= QUAD_SIMT_M) quad_forms_simt(s, sigma, sigp_global, M, Kc, v, smem, emit);
+    if (M <= QUAD_SIMT_M) quad_forms_simt<8>(s, sigma, sigp_global, M, Kc, v, smem, emit);
     else quad_forms_mma(s, sigma, sigp_global, M, Kc, v, smem, emit);
 }
 
