@@ -133,9 +133,9 @@ __device__ inline void mma_pass(const FoldData &F, int K, int Kc, int R, int r0,
             }
             if (weighted) {
                 double *wd = dst + 8 * NT_MAX * LDS_C;
-                for (int idx = threadIdx.x; idx < 2 * KT; idx += T) {
-                    const int q = idx & (KT - 1), h = h0 + q;
-                    __pipeline_memcpy_async(wd + idx, (idx < KT ? wv : ev) + min(h, N - 1), 8, h < N ? 0 : 8);
+                for (int idx = threadIdx.x; idx < 2 * KT; idx += T) {     // (w[h], e[h]) interleaved: one 16-byte load per row
+                    const int q = idx >> 1, h = h0 + q;
+                    __pipeline_memcpy_async(wd + idx, ((idx & 1) ? ev : wv) + min(h, N - 1), 8, h < N ? 0 : 8);
                 }
             }
         }
@@ -242,10 +242,12 @@ __device__ inline void mma_pass(const FoldData &F, int K, int Kc, int R, int r0,
                         const int hl = 16 * g + 4 * ks + gk;
                         double a0 = xv[0][ks], a1 = xv[1][ks];
                         if (weighted) {
-                            const double w = wrow[hl], e = wrow[KT + hl];
-                            bb0 = fma(a0 * a0, w, bb0); bb1 = fma(a1 * a1, w, bb1);
+                            const double2 we = *reinterpret_cast<const double2 *>(wrow + 2 * hl);
+                            const double w = we.x, e = we.y;
                             ze0 = fma(a0, e, ze0); ze1 = fma(a1, e, ze1);
+                            const double x0 = a0, x1 = a1;
                             a0 *= w; a1 *= w;
+                            bb0 = fma(a0, x0, bb0); bb1 = fma(a1, x1, bb1);          // (x w) x: one multiply fewer than (x x) w, identical for genotype codes
                         }
                         aw0[ks] = a0; aw1[ks] = a1;
                     }
