@@ -3,34 +3,37 @@ usage: python scripts/make_profiles.py r01     (reads launches.csv, prof_binom_f
 import collections, csv, json, os, re, subprocess, sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+# optional: python scripts/make_profiles.py r01 <report.ncu-rep> <suffix> "<workload text>"  -> only profiles/<tag>_fit_kernel_<suffix>_ncu.md
+ALT = sys.argv[2:5] if len(sys.argv) >= 5 else None
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
 # ---- launch list ------------------------------------------------------------------------------
-rows = [r for r in csv.reader(open(os.path.join(G, "launches.csv"))) if len(r) > 10]
-hdr = rows[0]; ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
-agg = collections.defaultdict(lambda: [0, 0.0])
-for r in rows[1:]:
-    name = re.sub(r"\(.*", "", r[ik]).replace("<unnamed>::", "").replace("pareben::", "")
-    agg[name][0] += 1; agg[name][1] += float(r[iv]) / 1e6
-tot = sum(v[1] for v in agg.values())
-with open(os.path.join(P, f"{tag}_launches.md"), "w") as f:
-    f.write(f"# Round 1 -- ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu`\n\n"
-            "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv` (raw: `" + f"{tag}_launches_bench_steps2.csv`). "
-            "Per-launch times are cold-cache and serialised: compare shares.\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
-    for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        f.write(f"| `{k}` | {n} | {ms:.3f} | {100 * ms / tot:.2f} % |\n")
-    f.write("\nThe fit kernel is the only kernel of a step (`gpu_launches` = 1 per step); `dfma_peak_kernel`/`dmma_peak_kernel` are the FP64 peak "
-            "probes bench.py runs once before the timed region; the gather/transpose/scale/int8 kernels belong to `pareben_problem_create` "
-            "(e2e path and set-up).\n")
-with open(os.path.join(P, f"{tag}_launches_bench_steps2.csv"), "w") as f:
-    w = csv.writer(f); w.writerow(["id", "kernel", "grid", "block", "gpu__time_duration_ns"])
+if not ALT:
+    rows = [r for r in csv.reader(open(os.path.join(G, "launches.csv"))) if len(r) > 10]
+    hdr = rows[0]; ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
     for r in rows[1:]:
-        w.writerow([r[0], re.sub(r"\(.*", "", r[ik]), r[hdr.index("Grid Size")], r[hdr.index("Block Size")], r[iv]])
+        name = re.sub(r"\(.*", "", r[ik]).replace("<unnamed>::", "").replace("pareben::", "")
+        agg[name][0] += 1; agg[name][1] += float(r[iv]) / 1e6
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(P, f"{tag}_launches.md"), "w") as f:
+        f.write(f"# Round 1 -- ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu`\n\n"
+                "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv` (raw: `" + f"{tag}_launches_bench_steps2.csv`). "
+                "Per-launch times are cold-cache and serialised: compare shares.\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
+        for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {n} | {ms:.3f} | {100 * ms / tot:.2f} % |\n")
+        f.write("\nThe fit kernel is the only kernel of a step (`gpu_launches` = 1 per step); `dfma_peak_kernel`/`dmma_peak_kernel` are the FP64 peak "
+                "probes bench.py runs once before the timed region; the gather/transpose/scale/int8 kernels belong to `pareben_problem_create` "
+                "(e2e path and set-up).\n")
+    with open(os.path.join(P, f"{tag}_launches_bench_steps2.csv"), "w") as f:
+        w = csv.writer(f); w.writerow(["id", "kernel", "grid", "block", "gpu__time_duration_ns"])
+        for r in rows[1:]:
+            w.writerow([r[0], re.sub(r"\(.*", "", r[ik]), r[hdr.index("Grid Size")], r[hdr.index("Block Size")], r[iv]])
 
 # ---- full capture -----------------------------------------------------------------------------
-rep = os.path.join(G, "prof_binom_full.ncu-rep")
+rep = ALT[0] if ALT else os.path.join(G, "prof_binom_full.ncu-rep")
 raw = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
 h, u, v = raw[0], raw[1], raw[2]
 want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
@@ -48,7 +51,7 @@ def num(k):
     x, un = val[k]; x = float(x.replace(",", ""))
     return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(un, 1.0)
 dr, dw = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
-json.dump({"kernel": "eben_fit_kernel<EPIS=0,BINOMIAL=1>", "workload": "config 2 full grid, 2000 fits, one launch (scripts/profile_case.py binomial 2000)",
+if not ALT: json.dump({"kernel": "eben_fit_kernel<EPIS=0,BINOMIAL=1>", "workload": "config 2 full grid, 2000 fits, one launch (scripts/profile_case.py binomial 2000)",
            "dram_bytes_read": dr, "dram_bytes_write": dw, "dram_bytes_per_launch": dr + dw, "ncu_duration_ms": float(val["gpu__time_duration.sum"][0]),
            "source": f"ncu --set full --clock-control none, gpurun_out/prof_binom_full.ncu-rep ({tag})"}, open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
 
@@ -92,8 +95,13 @@ alg = None
 try:
     for ln in open(os.path.join(G, "plain_profile_full.log")): alg = ln.strip()
 except OSError: pass
-with open(os.path.join(P, f"{tag}_fit_kernel_ncu.md"), "w") as f:
-    f.write("# Round 1 -- ncu `--set full` of the fit kernel on the bench workload\n\n"
+out_md = os.path.join(P, f"{tag}_fit_kernel_{ALT[1]}_ncu.md" if ALT else f"{tag}_fit_kernel_ncu.md")
+with open(out_md, "w") as f:
+    if ALT:
+        f.write(f"# Round 1 -- ncu `--set full` of the fit kernel: {ALT[2]}\n\n| metric | value | unit |\n|---|---|---|\n")
+        alg = None
+    else:
+        f.write("# Round 1 -- ncu `--set full` of the fit kernel on the bench workload\n\n"
             "Command (on the B200 box, after the same command exited 0 without ncu): `ncu --set full --clock-control none --import-source on "
             "-k regex:eben_fit -s 1 -c 1 python scripts/profile_case.py binomial 2000`  \n"
             "Workload: config 2, all 2,000 fits, ONE launch of `eben_fit_kernel<EPIS=0,BINOMIAL=1>` (hybrid kernel: DMMA contraction fed by a cp.async ring, "
@@ -113,6 +121,7 @@ with open(os.path.join(P, f"{tag}_fit_kernel_ncu.md"), "w") as f:
     f.write("```\n")
 
 # ---- bench lines and parity table ---------------------------------------------------------------
+if ALT: print(open(out_md).read()[:3000]); sys.exit(0)
 for a, b in (("bench.json", f"{tag}_bench_n1.json"), ("bench_reference.json", f"{tag}_bench_reference_n1.json"), ("parity.md", f"{tag}_parity.md")):
     if os.path.exists(os.path.join(G, a)): open(os.path.join(P, b), "w").write(open(os.path.join(G, a)).read())
-print(open(os.path.join(P, f"{tag}_fit_kernel_ncu.md")).read()[:6000])
+print(open(out_md).read()[:6000])
