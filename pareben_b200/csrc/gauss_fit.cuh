@@ -431,23 +431,24 @@ __device__ inline void contract_col(const FoldData &F, int K, int Kc, ColVal col
     __syncthreads();
     bool dv = false;
     double *row = dest(0, dv);
-    auto partial = [&](const Cand<EPIS> &cd, int p4, double (&z)[4]) {
+    // int8: all the words a lane needs from both candidates for 1024 positions are requested before the first is used
+    // (up to 32 loads in flight per lane: the matrix comes from L2, a dependent load per 128 positions would pay its
+    // latency eight times per candidate); f64: one 128-position step at a time.
+    constexpr int CH = 8;
+    auto accumulate = [&](const Cand<EPIS> &cd, int wi, int wj, int p4, double (&z)[4]) {
         const double4 v = *reinterpret_cast<const double4 *>(sV + p4);
-        double x[4];
-        if (X8) {
-            const int wi = *reinterpret_cast<const int *>(X8 + (size_t)cd.i * ldt + p4);
-            const int wj = (EPIS && cd.i != cd.j) ? *reinterpret_cast<const int *>(X8 + (size_t)cd.j * ldt + p4) : 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) x[b] = cd.from_words(wi, wj, b);
-        } else {
-            const double2 *pi = reinterpret_cast<const double2 *>(Xd + (size_t)cd.i * ldt + p4);
-            const double2 a = pi[0], c = pi[1];
-            x[0] = a.x; x[1] = a.y; x[2] = c.x; x[3] = c.y;
-            if (EPIS && cd.i != cd.j) {
-                const double2 *pj = reinterpret_cast<const double2 *>(Xd + (size_t)cd.j * ldt + p4);
-                const double2 e = pj[0], f = pj[1];
-                x[0] *= e.x; x[1] *= e.y; x[2] *= f.x; x[3] *= f.y;
-            }
+        z[0] = fma(cd.from_words(wi, wj, 0), v.x, z[0]); z[1] = fma(cd.from_words(wi, wj, 1), v.y, z[1]);
+        z[2] = fma(cd.from_words(wi, wj, 2), v.z, z[2]); z[3] = fma(cd.from_words(wi, wj, 3), v.w, z[3]);
+    };
+    auto partial_f64 = [&](const Cand<EPIS> &cd, int p4, double (&z)[4]) {
+        const double4 v = *reinterpret_cast<const double4 *>(sV + p4);
+        const double2 *pi = reinterpret_cast<const double2 *>(Xd + (size_t)cd.i * ldt + p4);
+        const double2 a = pi[0], c = pi[1];
+        double x[4] = {a.x, a.y, c.x, c.y};
+        if (EPIS && cd.i != cd.j) {
+            const double2 *pj = reinterpret_cast<const double2 *>(Xd + (size_t)cd.j * ldt + p4);
+            const double2 e = pj[0], f = pj[1];
+            x[0] *= e.x; x[1] *= e.y; x[2] *= f.x; x[3] *= f.y;
         }
         z[0] = fma(x[0], v.x, z[0]); z[1] = fma(x[1], v.y, z[1]); z[2] = fma(x[2], v.z, z[2]); z[3] = fma(x[3], v.w, z[3]);
     };
@@ -456,7 +457,30 @@ __device__ inline void contract_col(const FoldData &F, int K, int Kc, ColVal col
         const bool two = c1 < Kc;
         Cand<EPIS> cda(c0, K), cdb(two ? c1 : c0, K);
         double za[4] = {0.0, 0.0, 0.0, 0.0}, zb[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int p4 = 4 * lane; p4 < ldt; p4 += 128) { partial(cda, p4, za); partial(cdb, p4, zb); }
+        if (X8) {
+            const int8_t *ai = X8 + (size_t)cda.i * ldt, *aj = X8 + (size_t)cda.j * ldt;
+            const int8_t *bi = X8 + (size_t)cdb.i * ldt, *bj = X8 + (size_t)cdb.j * ldt;
+            const bool pa = EPIS && cda.i != cda.j, pb = EPIS && cdb.i != cdb.j;
+            for (int base = 4 * lane; base < ldt; base += 128 * CH) {
+                int wai[CH], waj[CH], wbi[CH], wbj[CH];
+#pragma unroll
+                for (int u = 0; u < CH; u++) {
+                    const int p4 = base + 128 * u;
+                    const bool in = p4 < ldt;
+                    wai[u] = in ? *reinterpret_cast<const int *>(ai + p4) : 0;
+                    wbi[u] = in ? *reinterpret_cast<const int *>(bi + p4) : 0;
+                    waj[u] = (in && pa) ? *reinterpret_cast<const int *>(aj + p4) : 0;
+                    wbj[u] = (in && pb) ? *reinterpret_cast<const int *>(bj + p4) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < CH; u++) {
+                    const int p4 = base + 128 * u;
+                    if (p4 < ldt) { accumulate(cda, wai[u], waj[u], p4, za); accumulate(cdb, wbi[u], wbj[u], p4, zb); }
+                }
+            }
+        } else {
+            for (int p4 = 4 * lane; p4 < ldt; p4 += 128) { partial_f64(cda, p4, za); partial_f64(cdb, p4, zb); }
+        }
         const double ta = warp_sum((za[0] + za[1]) + (za[2] + za[3])), tb = warp_sum((zb[0] + zb[1]) + (zb[2] + zb[3]));
         if (lane == 0) {
             row[c0] = dv ? ta / F.scale[c0] : ta;
