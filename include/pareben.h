@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PAREBEN_VERSION 1
+#define PAREBEN_VERSION 2
 
 /* prior (R: prior = "gaussian" | "binomial", R/CrossValidate.R:65,87) */
 #define PAREBEN_GAUSSIAN 0
@@ -77,13 +77,20 @@ int pareben_run_fits(pareben_problem *p, int n_fits, const int *fold, const doub
  * R/CrossValidate.R:66-70 / 88-92.  Grid point g (alpha[g], lambda[g]) x fold f (1..n_folds)
  * is fit number g*n_folds + (f-1).  fold_err/status/n_selected are n_grid*n_folds, grid-major,
  * fold-minor -- the row order of Results.Detail.
- * Sharding (one process per GPU): fits are ordered by falling expected cost (rising lambda)
- * and dealt round-robin over n_shards; this call computes shard `shard` on `device` and writes
- * ONLY those entries of the outputs (pass shard 0, n_shards 1 for everything).  The caller
- * merges shards -- a 32 KB gather at nFolds = 10, the `.combine = rbind` of the reference. */
+ * Devices: the call drives n_devices GPUs, `device` .. `device + n_devices - 1` (n_devices = 0: every
+ * visible device from `device` on), one internal worker thread per GPU, BASIS uploaded once per
+ * GPU; it returns when all of them have written their entries (the in-library gather).  This is
+ * what a single R process uses to fan one grid over the box (the reference fans the 400 rows over
+ * all registered workers from one call, R/CrossValidate.R:66-70).
+ * Shards (one process per GPU, e.g. torchrun / doMPI-style launches): fits are ordered by falling
+ * expected cost (rising lambda) and dealt round-robin over n_shards * n_devices; this call computes
+ * shard `shard` and writes ONLY those entries of the outputs (pass shard 0, n_shards 1 for
+ * everything).  The caller merges shards -- a 32 KB gather at nFolds = 10, the `.combine = rbind`
+ * of the reference.  Each fit is computed by exactly one thread block with a schedule-independent
+ * summation order, so the table is bitwise identical for any device / shard count. */
 int pareben_cv_grid(const double *basis, int n, int k, const double *target, const int *fold_id,
                     int n_folds, const double *alpha, const double *lambda, int n_grid, int epis,
-                    int prior, int device, int shard, int n_shards, double *fold_err,
+                    int prior, int n_devices, int device, int shard, int n_shards, double *fold_err,
                     int *status, int *n_selected);
 
 /* The shard assignment pareben_cv_grid uses, exposed for the host layer and tests (host-only

@@ -6,6 +6,6 @@ wrappers EBelasticNet_Gaussian / EBelasticNet_Binomial.  All numerics run in lib
 (pareben_b200/csrc, C-ABI in include/pareben.h); there is no CPU implementation here.
 """
 from ._lib import (FIT_BASIS_CAP, FIT_ITER_MAX, FIT_NONFINITE, FIT_NOT_PD, ParebenError, Problem, cv_grid,  # noqa: F401
-                   device_count, load, measure_fp64_peak, shard_plan)
+                   default_device, device_count, load, measure_fp64_peak, release_cache, shard_plan)
 from .cross_validate import (AssignToFolds, BuildGrid, CrossValidate, EBelasticNet_Binomial,  # noqa: F401
                              EBelasticNet_Gaussian, GetLambdaMax, LocalSearch, SLFilter)

@@ -28,7 +28,8 @@ SIGNATURES = {
     "pareben_release_cache": (None, []),
     "pareben_run_fits": (ctypes.c_int, [_vp, ctypes.c_int, _ip, _dp, _dp, _dp, _ip, _ip, _ip]),
     "pareben_cv_grid": (ctypes.c_int, [_dp, ctypes.c_int, ctypes.c_int, _dp, _ip, ctypes.c_int, _dp, _dp, ctypes.c_int,
-                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _ip, _ip]),
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _ip,
+                                       _ip]),
     "pareben_shard_plan": (ctypes.c_int, [_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _ip, _ip]),
     "pareben_fit": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, _dp, _dp, _dp, _dp, _ip]),
     "pareben_lambda_max": (ctypes.c_int, [_vp, _dp]),
@@ -80,12 +81,27 @@ def device_count() -> int:
     return load().pareben_device_count()
 
 
+def release_cache() -> None:
+    """Give the library's idle device buffers back to the driver (pareben_release_cache)."""
+    load().pareben_release_cache()
+
+
+def default_device() -> int:
+    """Device used when the caller does not name one: LOCAL_RANK under a one-process-per-GPU launcher
+    (torchrun), else 0 -- so that ranks started with default arguments do not all land on cuda:0."""
+    try:
+        return int(os.environ.get("LOCAL_RANK", "0"))
+    except ValueError:
+        return 0
+
+
 class Problem:
     """One CrossValidate problem resident on a GPU (pareben_problem_create)."""
 
     def __init__(self, BASIS, Target, fold_id=None, n_folds: int = 0, epis: bool = False, prior: str = "gaussian",
-                 device: int = 0):
+                 device: int | None = None):
         lib = load()
+        device = default_device() if device is None else int(device)
         self._X = np.asfortranarray(np.asarray(BASIS, dtype=np.float64))
         self._y = np.ascontiguousarray(np.asarray(Target, dtype=np.float64).ravel())
         n, k = self._X.shape
@@ -124,6 +140,21 @@ class Problem:
         _check(load().pareben_run_fits(self._h, m, _i(fold), _d(alpha), _d(lam), _d(err), _i(st), _i(ns), _i(it)))
         return err, st, ns, it
 
+    def cv_grid(self, alpha, lam, shard: int = 0, n_shards: int = 1):
+        """The grid call on a problem that is already resident (BuildGrid's lambda_max and the fits share one
+        upload): same table layout and the same shard assignment as pareben_cv_grid; entries of other shards stay 0."""
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        if alpha.size != lam.size or self.n_folds < 1:
+            raise ValueError("alpha and lambda must have equal length and the problem must have folds")
+        nf, total = self.n_folds, alpha.size * self.n_folds
+        mine = shard_plan(lam, nf, shard, n_shards)
+        err = np.zeros(total); st = np.zeros(total, np.int32); ns = np.zeros(total, np.int32)
+        if mine.size:
+            e, s_, n_, _ = self.run_fits(mine % nf + 1, alpha[mine // nf], lam[mine // nf])
+            err[mine] = e; st[mine] = s_; ns[mine] = n_
+        return err.reshape(alpha.size, nf), st.reshape(alpha.size, nf), ns.reshape(alpha.size, nf)
+
     def fit(self, alpha: float, lam: float):
         """Batch-of-1 final model: returns (beta_table, wald, intercept, extra, status)."""
         k = self.k
@@ -157,20 +188,34 @@ class Problem:
         return float(fl[0]), float(ms[0]), int(ln[0])
 
 
-def cv_grid(BASIS, Target, fold_id, n_folds, alpha, lam, epis=False, prior="gaussian", device=0,
-            shard=0, n_shards=1):
+def cv_grid(BASIS, Target, fold_id, n_folds, alpha, lam, epis=False, prior="gaussian", device=None,
+            shard=0, n_shards=1, n_devices=1):
     """pareben_cv_grid: host buffers in, per-fit hold-out errors out (grid-major, fold-minor).
-    Entries owned by other shards are left 0 so that shards merge by summation."""
+    n_devices GPUs starting at `device` share the call (0 = all visible).  Entries owned by other shards are left 0
+    so that shards merge by summation."""
     X = np.asfortranarray(np.asarray(BASIS, dtype=np.float64))
     y = np.ascontiguousarray(np.asarray(Target, dtype=np.float64).ravel())
     fid = np.ascontiguousarray(np.asarray(fold_id, dtype=np.int32).ravel())
     alpha = np.ascontiguousarray(alpha, dtype=np.float64)
     lam = np.ascontiguousarray(lam, dtype=np.float64)
+    if X.ndim != 2:
+        raise ValueError("BASIS must be a matrix")
     n, k = X.shape
+    n_folds = int(n_folds)
+    # the C side only sees pointers: every length is checked here
+    if y.size != n:
+        raise ValueError("Target length must equal nrow(BASIS)")
+    if fid.size != n:
+        raise ValueError("fold_id length must equal nrow(BASIS)")
+    if alpha.size != lam.size or alpha.size < 1:
+        raise ValueError("alpha and lambda must be non-empty and of equal length")
+    if n_folds < 1:
+        raise ValueError("n_folds must be >= 1")
+    device = default_device() if device is None else int(device)
     total = alpha.size * n_folds
     err = np.zeros(total); st = np.zeros(total, np.int32); ns = np.zeros(total, np.int32)
     _check(load().pareben_cv_grid(_d(X), n, k, _d(y), _i(fid), n_folds, _d(alpha), _d(lam), alpha.size, int(bool(epis)),
-                                  GAUSSIAN if prior == "gaussian" else BINOMIAL, device, shard, n_shards,
+                                  GAUSSIAN if prior == "gaussian" else BINOMIAL, int(n_devices), device, shard, n_shards,
                                   _d(err), _i(st), _i(ns)))
     return err.reshape(alpha.size, n_folds), st.reshape(alpha.size, n_folds), ns.reshape(alpha.size, n_folds)
 

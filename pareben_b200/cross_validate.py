@@ -35,21 +35,26 @@ def _as_matrix(BASIS):
     return X
 
 
-def GetLambdaMax(BASIS, Target, Epis="no", device: int = 0) -> float:
+def GetLambdaMax(BASIS, Target, Epis="no", device: int | None = None) -> float:
     """GetLambdaMax (BuildGrid.R:5-32) on the device; the Epis pair scan (K^2/2 columns generated on
     the fly) is the part that is quadratic in K."""
     with _lib.Problem(_as_matrix(BASIS), Target, None, 0, Epis == "yes", "gaussian", device) as p:
         return p.lambda_max()
 
 
-def BuildGrid(BASIS, Target, nFolds=0, Epis="no", device: int = 0):
-    """BuildGrid (BuildGrid.R:34-52) -> dict(alpha=[400], lambda=[400]) in expand.grid order (alpha fastest)."""
-    lam_max = GetLambdaMax(BASIS, Target, Epis, device) * 10
+def _grid_from_lambda_max(lam_max: float):
+    """The 20 x 20 grid of BuildGrid.R:36-51 from GetLambdaMax's value: expand.grid order (alpha fastest)."""
+    lam_max = lam_max * 10
     lam_min = math.log(0.001 * lam_max)
     step = (math.log(lam_max) - lam_min) / 19
     Lambda = np.exp(rcompat.seq(math.log(lam_max), lam_min, -step))
     Alpha = rcompat.seq(1.0, 0.05, -0.05)
     return {"alpha": np.tile(Alpha, Lambda.size), "lambda": np.repeat(Lambda, Alpha.size)}
+
+
+def BuildGrid(BASIS, Target, nFolds=0, Epis="no", device: int | None = None):
+    """BuildGrid (BuildGrid.R:34-52) -> dict(alpha=[400], lambda=[400]) in expand.grid order (alpha fastest)."""
+    return _grid_from_lambda_max(GetLambdaMax(BASIS, Target, Epis, device))
 
 
 def AssignToFolds(BASIS, nFolds=0, foldId=0, sample_kind: str = "Rejection", rng: rcompat.RRandom | None = None):
@@ -74,22 +79,57 @@ def _dist():
     return None
 
 
-def _grid_errors(X, y, fold_id, n_folds, alpha, lam, epis, prior, device):
-    """All n_grid x n_folds hold-out errors; sharded over ranks when torch.distributed is up."""
+def _merge_shards(err, st, ns, device):
+    """The `.combine = rbind` of the reference across ranks: every rank filled only its own entries (the rest are 0),
+    so one all-reduce(sum) of the three small tables is the gather.  No-op without an initialised process group."""
     dist = _dist()
     if dist is None:
-        return _lib.cv_grid(X, y, fold_id, n_folds, alpha, lam, epis, prior, device)
+        return err, st, ns
     import torch
-    rank, world = dist.get_rank(), dist.get_world_size()
-    err, st, ns = _lib.cv_grid(X, y, fold_id, n_folds, alpha, lam, epis, prior, device, rank, world)
     on_gpu = dist.get_backend() == "nccl"
-    dev = torch.device("cuda", device) if on_gpu else torch.device("cpu")
+    dev = torch.device("cuda", _lib.default_device() if device is None else device) if on_gpu else torch.device("cpu")
     packed = torch.from_numpy(np.concatenate([err.ravel(), st.ravel().astype(np.float64), ns.ravel().astype(np.float64)])).to(dev)
-    dist.all_reduce(packed)            # entries are disjoint per rank -> the sum is the gather
+    dist.all_reduce(packed)
     packed = packed.cpu().numpy()
     m = err.size
     return (packed[:m].reshape(err.shape), packed[m:2 * m].astype(np.int32).reshape(err.shape),
             packed[2 * m:].astype(np.int32).reshape(err.shape))
+
+
+def _grid_and_errors(X, y, fold_id, n_folds, Epis, prior, device, n_devices=1):
+    """BuildGrid + all n_grid x n_folds hold-out errors.  One process, one GPU: BASIS is uploaded ONCE and the same
+    resident problem serves GetLambdaMax and the fits.  n_devices != 1: one call fans the grid over that many GPUs of
+    this process (pareben_cv_grid's worker threads).  With torch.distributed up (one process per GPU) every rank
+    computes its shard and the shards are merged by _merge_shards."""
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+    epis = Epis == "yes"
+    if n_devices != 1:
+        grid = BuildGrid(X, y, n_folds, Epis, device)
+        err, st, ns = _lib.cv_grid(X, y, fold_id, n_folds, grid["alpha"], grid["lambda"], epis, prior, device, rank, world, n_devices)
+    else:
+        with _lib.Problem(X, y, fold_id, n_folds, epis, prior, device) as p:
+            grid = _grid_from_lambda_max(p.lambda_max())
+            err, st, ns = p.cv_grid(grid["alpha"], grid["lambda"], rank, world)
+    err, st, ns = _merge_shards(err, st, ns, device)
+    return grid, err, st, ns
+
+
+def _which_min(values, status, what):
+    """R's which.min: first minimum, NA skipped.  A table that is all NA stops, as the reference does on
+    is.na(Mu0); fits that ended with a non-zero status are reported (the reference prints and carries on)."""
+    bad = np.asarray(status) != 0
+    if bad.any():
+        import warnings
+        st = np.asarray(status)
+        warnings.warn(f"{int(bad.sum())} of {st.size} fits finished with a non-zero status "
+                      f"(basis cap {int((st & _lib.FIT_BASIS_CAP > 0).sum())}, not positive definite {int((st & _lib.FIT_NOT_PD > 0).sum())}, "
+                      f"non-finite {int((st & _lib.FIT_NONFINITE > 0).sum())}, iteration limit {int((st & _lib.FIT_ITER_MAX > 0).sum())})",
+                      RuntimeWarning, stacklevel=3)
+    values = np.asarray(values, dtype=np.float64)
+    if np.all(np.isnan(values)):
+        raise ValueError(f"every {what} is NA: no optimum can be selected")
+    return int(np.nanargmin(values))
 
 
 def _summarise(alpha, lam, fold_err, value_name):
@@ -104,30 +144,31 @@ def _summarise(alpha, lam, fold_err, value_name):
 
 
 def CrossValidate(BASIS, Target, nFolds, foldId=0, Epis="no", prior="gaussian", search="global",
-                  device: int = 0, sample_kind: str = "Rejection"):
-    """CrossValidate (CrossValidate.R:61-117).  Returns a dict with the reference's four entries."""
+                  device: int | None = None, sample_kind: str = "Rejection", n_devices: int = 1):
+    """CrossValidate (CrossValidate.R:61-117).  Returns a dict with the reference's four entries.
+    device: GPU of this process (default LOCAL_RANK, else 0); n_devices: GPUs this ONE call fans the grid over."""
     X = _as_matrix(BASIS)
     y = np.asarray(Target, dtype=np.float64).ravel()
     prior_key = "gaussian" if prior == "gaussian" else "binomial"     # anything else = binomial branch (:65,87)
     if search != "global":
-        return LocalSearch(X, y, nFolds, Epis, foldId, prior, device=device, sample_kind=sample_kind)
-    grid = BuildGrid(X, y, nFolds, Epis, device)
+        return LocalSearch(X, y, nFolds, Epis, foldId, prior, device=device, sample_kind=sample_kind, n_devices=n_devices)
     # TestModel ignores the caller's foldId and recomputes folds with set.seed(1) (TestModel.R:9)
     folds = AssignToFolds(X, nFolds, sample_kind=sample_kind)
-    err, status, nsel = _grid_errors(X, y, folds, nFolds, grid["alpha"], grid["lambda"], Epis == "yes", prior_key, device)
+    grid, err, status, nsel = _grid_and_errors(X, y, folds, nFolds, Epis, prior_key, device, n_devices)
     n_grid = grid["alpha"].size
     value = "MSE" if prior_key == "gaussian" else "logL"
     detail = {"foldId": np.tile(np.arange(1, nFolds + 1), n_grid), "alpha": np.repeat(grid["alpha"], nFolds),
               "lambda": np.repeat(grid["lambda"], nFolds), value: err.ravel().copy()}
     summary = _summarise(grid["alpha"], grid["lambda"], err, "MSE" if prior_key == "gaussian" else "Likelihood")
-    idx = int(np.argmin(summary["MSE" if prior_key == "gaussian" else "Likelihood"]))   # which.min (:78, intent of :99)
+    col = "MSE" if prior_key == "gaussian" else "Likelihood"
+    idx = _which_min(summary[col], status, col)                                          # which.min (:78, intent of :99)
     return {"Results.Detail": detail, "Results.Summary": summary,
             "lambda.optimal": float(summary["lambda"][idx]), "alpha.optimal": float(summary["alpha"][idx]),
             "status": status, "n_selected": nsel, "foldId": folds}
 
 
-def LocalSearch(BASIS, Target, nFolds, Epis="no", foldId=0, prior="gaussian", device: int = 0,
-                sample_kind: str = "Rejection", rng: rcompat.RRandom | None = None):
+def LocalSearch(BASIS, Target, nFolds, Epis="no", foldId=0, prior="gaussian", device: int | None = None,
+                sample_kind: str = "Rejection", rng: rcompat.RRandom | None = None, n_devices: int = 1):
     """LocalSearch (LocalSearch.R:6-130).  Every fit is independent of visiting order, so the whole
     alpha x lambda x fold table is computed in one batched launch and the early-stopping walk
     (:56-122) is replayed over it; rows the walk never reaches stay zero in fullCV, as in the
@@ -137,8 +178,7 @@ def LocalSearch(BASIS, Target, nFolds, Epis="no", foldId=0, prior="gaussian", de
     y = np.asarray(Target, dtype=np.float64).ravel()
     prior_key = "gaussian" if prior == "gaussian" else "binomial"
     folds = AssignToFolds(X, nFolds, foldId, sample_kind, rng)
-    grid = BuildGrid(X, y, nFolds, Epis, device)
-    err, status, nsel = _grid_errors(X, y, folds, nFolds, grid["alpha"], grid["lambda"], Epis == "yes", prior_key, device)
+    grid, err, status, nsel = _grid_and_errors(X, y, folds, nFolds, Epis, prior_key, device, n_devices)
     if prior_key == "binomial":
         err = -err                       # walk on Likelihood = -logL (documented deviation)
     Alpha, Lambda = grid["alpha"][:20], grid["lambda"][::20]
@@ -150,7 +190,7 @@ def LocalSearch(BASIS, Target, nFolds, Epis="no", foldId=0, prior="gaussian", de
         sse = np.full((n_step, 2), 1e10)
         for i_s in range(n_step):
             upto = i_s if i_s >= 1 else 1            # SSE1Alpha[1:(i_s-1),1]; 1:0 selects row 1
-            mi = int(np.argmin(sse[:upto, 0]))
+            mi = int(np.nanargmin(sse[:upto, 0]))    # which.min skips NA; rows not yet visited hold 1e10
             previous = sse[mi, 0] + sse[mi, 1]
             fe = err[i_s * 20 + ia]
             m, se = rcompat.mean(fe), rcompat.sd(fe) / math.sqrt(nFolds)
@@ -159,9 +199,9 @@ def LocalSearch(BASIS, Target, nFolds, Epis="no", foldId=0, prior="gaussian", de
             step += 1
             if m - previous > 0:
                 break
-        idx = int(np.argmin(sse[:, 0]))
+        idx = int(np.nanargmin(sse[:, 0]))
         each[ia] = (Alpha[ia], Lambda[idx], sse[idx, 0], sse[idx, 1])
-    idx = int(np.argmin(each[:, 2]))
+    idx = _which_min(each[:, 2], status, "per-alpha minimum")
     return {"CrossValidation": each, "alpha.optimal": float(each[idx, 0]), "lambda.optimal": float(each[idx, 1]),
             "fullCV": full, "status": status, "foldId": folds}
 
@@ -180,7 +220,7 @@ def _weight_table(table, keep, epis, n):
     return np.column_stack([blup, t, p])
 
 
-def EBelasticNet_Gaussian(BASIS, Target, lam, alpha, Epis="no", verbose=0, device: int = 0):
+def EBelasticNet_Gaussian(BASIS, Target, lam, alpha, Epis="no", verbose=0, device: int | None = None):
     """EBelasticNet.Gaussian (EBelasticNet.Gaussian.R:1-101) through pareben_fit (batch of 1, all rows)."""
     X = _as_matrix(BASIS)
     epis = Epis == "yes"
@@ -191,7 +231,7 @@ def EBelasticNet_Gaussian(BASIS, Target, lam, alpha, Epis="no", verbose=0, devic
             "residVar": resid, "lambda": lam, "alpha": alpha, "status": status}
 
 
-def EBelasticNet_Binomial(BASIS, Target, lam, alpha, Epis="no", verbose=0, device: int = 0):
+def EBelasticNet_Binomial(BASIS, Target, lam, alpha, Epis="no", verbose=0, device: int | None = None):
     """EBelasticNet.Binomial (EBelasticNet.Binomial.R:1-85) through pareben_fit."""
     X = _as_matrix(BASIS)
     epis = Epis == "yes"
@@ -202,7 +242,7 @@ def EBelasticNet_Binomial(BASIS, Target, lam, alpha, Epis="no", verbose=0, devic
             "Intercept": icpt.copy(), "lambda": lam, "alpha": alpha, "status": status}
 
 
-def SLFilter(BASIS, Target, tau_main: float = 0.02, tau_pair: float = 0.05, Epis: str = "yes", device: int = 0):
+def SLFilter(BASIS, Target, tau_main: float = 0.02, tau_pair: float = 0.05, Epis: str = "yes", device: int | None = None):
     """The single-locus prefilter that precedes CrossValidate in the published workflow
     (paper_materials/Real Data Analysis/SL_filter.R:17-52): standardised-correlation screening of the main-effect
     columns (> tau_main) and, for Epis="yes", of all pairwise products (> tau_pair), on the device.

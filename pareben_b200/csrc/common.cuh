@@ -52,7 +52,16 @@ struct Problem {
     const FoldData *folds;   // [n_folds + 1]; index 0 = all rows, f = rows with fold_id != f
 };
 
-struct FitTask { int fold; double alpha, lambda; int out_index; };
+struct FitTask { int fold; double alpha, lambda; int out_index; int group; };
+
+// Device-side scheduler state of one launch (see next_task() in fit_kernel.cuh).  Fits that differ only in the
+// fold (same alpha, lambda: one row of the reference's ParameterGrid, R/CrossValidate.R:66) form a group and
+// cost about the same, so the first fit of a group to run is the pilot that prices its siblings.
+struct Sched {
+    int *taken;                      // [n_tasks] 0 = free, 1 = claimed
+    unsigned long long *t_start;     // [n_groups] %globaltimer at which the group's first fit started (0 = none yet)
+    unsigned long long *cost;        // [n_groups] longest finished fit of the group in ns (0 = none yet)
+};
 
 struct FitOutputs {
     double *fold_err;        // [n] indexed by out_index

@@ -22,9 +22,84 @@ constexpr int QUAD_DOUBLES = cmax(2 * QT * LDS_V + 784, cmax(4096 + 1040, GRAM_P
 constexpr int S_BUF_DOUBLES = cmax(cmax(cmax(SWEEP_DOUBLES, SWEEP_PANEL_DOUBLES), cmax(SV_DOUBLES, COL_MAX_ROWS)), cmax(GRAM_DOUBLES, QUAD_DOUBLES));
 constexpr size_t S_BUF_BYTES = (size_t)S_BUF_DOUBLES * sizeof(double);
 
+__device__ inline unsigned long long sched_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Longest-predicted-first task selection with on-line cost learning.  Fit cost varies > 100x over the grid and does
+// not follow lambda alone (it peaks where the active set and the iteration count are both large), so a queue in a fixed
+// order leaves most SMs idle behind a few long fits started late.  Here a block that needs work scans the unclaimed
+// tasks and takes the one with the largest predicted cost:
+//   * a group (grid point) none of whose fits has started: top priority, in host order (rising lambda) -- every
+//     group gets a pilot as early as possible;
+//   * a group whose pilot is still running: the pilot's elapsed time so far (a lower bound that keeps growing, so
+//     the siblings of long fits are pulled forward while the pilot is still busy);
+//   * a group with a finished fit: the longest finished duration.
+// The first pull of a block is its own index (tasks arrive with the pilots first), which avoids a start-up stampede.
+// The result table does not depend on the schedule: every fit is computed by one block on its own.
+__device__ inline int next_task(const FitTask *__restrict__ tasks, int n_tasks, const Sched &sd, bool first, const Scratch &sc,
+                                int *s_pick)
+{
+    const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+    volatile int *taken = sd.taken;
+    volatile unsigned long long *cost = sd.cost, *tstart = sd.t_start;
+    for (int attempt = 0;; attempt++) {
+        int pick = -1;
+        if (first && attempt == 0) {
+            pick = (int)blockIdx.x < n_tasks ? (int)blockIdx.x : -1;
+        } else {
+            const unsigned long long now = sched_now();
+            unsigned long long bp = 0; int bi = 0x7fffffff;
+            for (int i = threadIdx.x; i < n_tasks; i += T) {
+                if (taken[i]) continue;
+                const int g = tasks[i].group;
+                const unsigned long long c = cost[g], t0 = tstart[g];
+                unsigned long long prio;
+                if (c) prio = c + 1;
+                else if (t0) prio = (now > t0 ? now - t0 : 0) + 1;
+                else prio = (1ull << 62) - (unsigned long long)i;
+                if (prio > bp || (prio == bp && i < bi)) { bp = prio; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+                const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (p2 > bp || (p2 == bp && i2 < bi)) { bp = p2; bi = i2; }
+            }
+            __syncthreads();
+            unsigned long long *redp = reinterpret_cast<unsigned long long *>(sc.red);
+            if (lane == 0) { redp[wid] = bp; sc.redi[wid] = bi; }
+            __syncthreads();
+            bp = 0; bi = 0x7fffffff;
+            for (int w = 0; w < nw; w++) {
+                const unsigned long long p2 = redp[w]; const int i2 = sc.redi[w];
+                if (p2 > bp || (p2 == bp && i2 < bi)) { bp = p2; bi = i2; }
+            }
+            pick = bp ? bi : -1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int got = -1;
+            if (pick >= 0) {
+                if (atomicCAS(sd.taken + pick, 0, 1) == 0) {
+                    got = pick;
+                    atomicCAS(sd.t_start + tasks[pick].group, 0ull, sched_now());
+                } else got = -2;                                   // lost the race: look again
+            }
+            *s_pick = got;
+        }
+        __syncthreads();
+        const int got = *s_pick;
+        if (got != -2) return got;
+    }
+}
+
 template <bool EPIS, bool BINOMIAL>
 __global__ void __launch_bounds__(FIT_THREADS, PAREBEN_MIN_BLOCKS)
-eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_tasks, int *queue, char *slabs,
+eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_tasks, Sched sched, char *slabs,
                 size_t slab_stride, FitOutputs out)
 {
     // One shared buffer (dynamic: it exceeds the 48 KB static limit), used by phases that never overlap: the
@@ -36,13 +111,11 @@ eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_t
     __shared__ int redi[66];
     __shared__ int s_task;
     Scratch sc{red, redi, s_buf};
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_task = atomicAdd(queue, 1);
-        __syncthreads();
-        const int ti = s_task;
-        if (ti >= n_tasks) break;
+    for (bool first = true;; first = false) {
+        const int ti = next_task(tasks, n_tasks, sched, first, sc, &s_task);
+        if (ti < 0) break;
         const FitTask task = tasks[ti];
+        const unsigned long long t_fit0 = sched_now();
         const FoldData F = P.folds[task.fold];
         Slab s = carve_slab(slabs + (size_t)blockIdx.x * slab_stride, P.cap, P.nmax, P.Kc);
 #ifdef PAREBEN_PHASE_TIMING
@@ -50,6 +123,7 @@ eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_t
 #endif
         if (BINOMIAL) binom_fit<EPIS>(P, F, v, s, task.lambda, task.alpha, task, out, sV, sc);
         else gauss_fit<EPIS>(P, F, v, s, task.lambda, task.alpha, task, out, sV, sc);
+        if (threadIdx.x == 0) atomicMax(sched.cost + task.group, sched_now() - t_fit0 + 1);
 #ifdef PAREBEN_PHASE_TIMING
         if (threadIdx.x == 0 && task.out_index < FIT_TRACE_MAX) g_fit_t1[task.out_index] = global_ns();
 #endif
@@ -59,12 +133,12 @@ eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_t
 
 template <bool EPIS, bool BINOMIAL>
 inline cudaError_t launch_fit_variant(int grid, int threads, cudaStream_t stream, const Problem &P, const Variant &v,
-                                      const FitTask *tasks, int n_tasks, int *queue, char *slabs, size_t slab_stride,
+                                      const FitTask *tasks, int n_tasks, const Sched &sched, char *slabs, size_t slab_stride,
                                       const FitOutputs &out)
 {
     cudaError_t e = cudaFuncSetAttribute(eben_fit_kernel<EPIS, BINOMIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_BUF_BYTES);
     if (e != cudaSuccess) return e;
-    eben_fit_kernel<EPIS, BINOMIAL><<<grid, threads, S_BUF_BYTES, stream>>>(P, v, tasks, n_tasks, queue, slabs, slab_stride, out);
+    eben_fit_kernel<EPIS, BINOMIAL><<<grid, threads, S_BUF_BYTES, stream>>>(P, v, tasks, n_tasks, sched, slabs, slab_stride, out);
     return cudaGetLastError();
 }
 
@@ -99,9 +173,9 @@ inline void timing_variant(unsigned long long *cycles_calls, int reset, unsigned
 #define PAREBEN_DEFINE_VARIANT(NAME, EPIS, BINOMIAL)                                                                      \
     namespace pareben {                                                                                                   \
     cudaError_t launch_fit_##NAME(int grid, int threads, cudaStream_t stream, const Problem &P, const Variant &v,        \
-                                  const FitTask *tasks, int n_tasks, int *queue, char *slabs, size_t slab_stride,         \
+                                  const FitTask *tasks, int n_tasks, const Sched &sched, char *slabs, size_t slab_stride,         \
                                   const FitOutputs &out)                                                                  \
-    { return launch_fit_variant<EPIS, BINOMIAL>(grid, threads, stream, P, v, tasks, n_tasks, queue, slabs, slab_stride, out); } \
+    { return launch_fit_variant<EPIS, BINOMIAL>(grid, threads, stream, P, v, tasks, n_tasks, sched, slabs, slab_stride, out); } \
     cudaError_t occupancy_##NAME(int *blocks_per_sm, int threads) { return occupancy_variant<EPIS, BINOMIAL>(blocks_per_sm, threads); } \
     void timing_##NAME(unsigned long long *cc, int reset, unsigned long long *t0, unsigned long long *t1, int *block, int n) \
     { timing_variant(cc, reset, t0, t1, block, n); }                                                                      \

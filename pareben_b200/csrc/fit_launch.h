@@ -8,7 +8,7 @@ constexpr int FIT_THREADS_HOST = 256;
 
 #define PAREBEN_DECLARE_VARIANT(NAME)                                                                                     \
     cudaError_t launch_fit_##NAME(int grid, int threads, cudaStream_t stream, const Problem &P, const Variant &v,        \
-                                  const FitTask *tasks, int n_tasks, int *queue, char *slabs, size_t slab_stride,         \
+                                  const FitTask *tasks, int n_tasks, const Sched &sched, char *slabs, size_t slab_stride,  \
                                   const FitOutputs &out);                                                                 \
     cudaError_t occupancy_##NAME(int *blocks_per_sm, int threads);                                                        \
     void timing_##NAME(unsigned long long *cc, int reset, unsigned long long *t0, unsigned long long *t1, int *block, int n);

@@ -8,6 +8,8 @@
 #include "fit_launch.h"
 
 #include <algorithm>
+#include <map>
+#include <thread>
 #include <chrono>
 #include <mutex>
 #include <cstdio>
@@ -52,14 +54,51 @@ void *pool_take(int device, size_t bytes, bool best_fit, size_t *got)
     return e.ptr;
 }
 
+// Parked bytes per device are capped (PAREBEN_POOL_MAX_MB, default 8 GiB): a buffer that would push the pool past
+// the cap goes straight back to the driver, so one huge problem does not starve the next one of a different size.
+size_t pool_cap_bytes()
+{
+    static size_t cap = [] { const char *e = getenv("PAREBEN_POOL_MAX_MB"); return (size_t)(e ? atoll(e) : 8192) << 20; }();
+    return cap;
+}
+
 void pool_give(int device, void *ptr, size_t bytes)
 {
     if (!ptr) return;
     std::lock_guard<std::mutex> lk(g_cache_mu);
     DevPool &pl = g_pool[device & 63];
-    if (pl.free_list.size() >= POOL_MAX_ENTRIES) { cudaFree(ptr); return; }
+    if (pl.free_list.size() >= POOL_MAX_ENTRIES || pl.parked + bytes > pool_cap_bytes()) { cudaFree(ptr); return; }
     pl.free_list.push_back(PoolEntry{ptr, bytes});
     pl.parked += bytes;
+}
+
+// Return every parked buffer of `device` to the driver (the current device must be `device`).
+size_t pool_release_device(int device)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    DevPool &pl = g_pool[device & 63];
+    const size_t freed = pl.parked;
+    for (const PoolEntry &e : pl.free_list) cudaFree(e.ptr);
+    pl.free_list.clear(); pl.parked = 0;
+    return freed;
+}
+
+size_t pool_parked(int device)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    return g_pool[device & 63].parked;
+}
+
+// cudaMalloc that, on failure, gives the pool's idle buffers back to the driver and tries once more.
+cudaError_t malloc_retry(int device, void **p, size_t bytes)
+{
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation && pool_parked(device) > 0) {
+        (void)cudaGetLastError();
+        pool_release_device(device);
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
 }
 
 #define CU(call)                                                                                  \
@@ -230,7 +269,6 @@ struct pareben_problem {
     std::vector<FoldData> h_folds;
     double *d_Xcol = nullptr, *d_y = nullptr;     // full data, column-major (kept for lambda_max)
     char *d_slabs = nullptr; size_t slab_stride = 0, slab_total = 0; int n_slabs = 0;
-    int *d_queue = nullptr;
     double *d_flops = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -241,7 +279,7 @@ struct pareben_problem {
     {
         const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
         void *p = pool_take(device, bytes, false, nullptr);
-        if (!p) CU(cudaMalloc(&p, bytes));
+        if (!p) CU(malloc_retry(device, &p, bytes));
         allocs.push_back(PoolEntry{p, bytes});
         return static_cast<T *>(p);
     }
@@ -311,6 +349,11 @@ static void ensure_slabs(pareben_problem *p)
     if (!p->d_slabs) {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
+        // idle pool buffers count as free: when the full-occupancy slab does not fit beside them they are released first
+        if ((size_t)per_sm * p->sm_count * p->slab_stride > free_b / 2 && pool_parked(p->device) > 0) {
+            pool_release_device(p->device);
+            CU(cudaMemGetInfo(&free_b, &total_b));
+        }
         while (per_sm > 1 && (size_t)per_sm * p->sm_count * p->slab_stride > free_b / 2) per_sm--;
         p->n_slabs = per_sm * p->sm_count;
         while (p->n_slabs > 1 && (size_t)p->n_slabs * p->slab_stride > free_b - (free_b >> 3)) p->n_slabs /= 2;   // huge problems: fewer blocks
@@ -318,7 +361,7 @@ static void ensure_slabs(pareben_problem *p)
         if (p->slab_total > free_b - (free_b >> 3))
             throw std::make_pair((int)PAREBEN_ENOMEM, std::string("per-block work slabs do not fit in device memory; lower PAREBEN_BASIS_CAP"));
         void *q = nullptr;
-        CU(cudaMalloc(&q, p->slab_total));
+        CU(malloc_retry(p->device, &q, p->slab_total));
         p->d_slabs = (char *)q;
     }
 }
@@ -438,7 +481,6 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         CU(cudaMemcpyAsync(p->d_folds, p->h_folds.data(), sizeof(FoldData) * (nf + 1), cudaMemcpyHostToDevice, p->stream));
 
         p->min_ntr = min_ntr;
-        p->d_queue = p->dalloc<int>(1);
         p->d_flops = p->dalloc<double>(1);
         CU(cudaStreamSynchronize(p->stream));
         lap("final sync");
@@ -454,14 +496,12 @@ extern "C" void pareben_problem_destroy(pareben_problem *p) { delete p; }
 
 extern "C" void pareben_release_cache(void)
 {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
     int cur = 0;
     cudaGetDevice(&cur);
     for (int d = 0; d < 64; d++) {
-        if (g_pool[d].free_list.empty()) continue;
+        if (pool_parked(d) == 0) continue;
         cudaSetDevice(d);
-        for (const PoolEntry &e : g_pool[d].free_list) cudaFree(e.ptr);
-        g_pool[d].free_list.clear(); g_pool[d].parked = 0;
+        pool_release_device(d);
     }
     cudaSetDevice(cur);
 }
@@ -482,23 +522,42 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
         CU(cudaSetDevice(p->device));
         ensure_slabs(p);
         std::vector<FitTask> tasks(n_fits);
+        // groups: fits that share (alpha, lambda) -- one row of the reference's ParameterGrid -- differ only in the fold
+        // and cost about the same; the device scheduler prices a group by its first finished fit (fit_kernel.cuh)
+        std::map<std::pair<double, double>, int> group_of;
         for (int i = 0; i < n_fits; i++) {
             if (fold[i] < 0 || fold[i] > p->n_folds || (p->n_folds > 0 && fold[i] == 0) || !p->h_folds[fold[i]].Xtr)
                 return fail(PAREBEN_EINVAL, "pareben_run_fits: fold label not available in this problem");
-            tasks[i] = FitTask{fold[i], alpha[i], lambda[i], i};
+            const auto key = std::make_pair(alpha[i], lambda[i]);
+            auto it = group_of.find(key);
+            if (it == group_of.end()) it = group_of.emplace(key, (int)group_of.size()).first;
+            tasks[i] = FitTask{fold[i], alpha[i], lambda[i], i, it->second};
         }
-        // expected cost grows as lambda falls (larger active sets): longest fits first
+        const int n_groups = (int)group_of.size();
+        // host order: rising lambda (larger active sets first) is the prior; one pilot per group goes to the front
         std::stable_sort(tasks.begin(), tasks.end(), [](const FitTask &a, const FitTask &b) { return a.lambda < b.lambda; });
+        {
+            std::vector<char> seen(n_groups, 0);
+            std::vector<FitTask> pilots, rest;
+            pilots.reserve(n_groups); rest.reserve(n_fits);
+            for (const FitTask &t : tasks) { if (!seen[t.group]) { seen[t.group] = 1; pilots.push_back(t); } else rest.push_back(t); }
+            tasks = pilots;
+            tasks.insert(tasks.end(), rest.begin(), rest.end());
+        }
         auto tmp_alloc = [&](size_t bytes) {
             bytes = (std::max<size_t>(bytes, 8) + 255) & ~(size_t)255;
             void *q = pool_take(p->device, bytes, false, nullptr);
-            if (!q) CU(cudaMalloc(&q, bytes));
+            if (!q) CU(malloc_retry(p->device, &q, bytes));
             scratch_bytes[ns] = bytes; scratch[ns++] = q; return q; };
         FitTask *d_tasks = (FitTask *)tmp_alloc(sizeof(FitTask) * n_fits);
         double *d_err = (double *)tmp_alloc(sizeof(double) * n_fits);
         int *d_ints = (int *)tmp_alloc(sizeof(int) * 3 * n_fits);
+        const size_t sched_bytes = sizeof(unsigned long long) * 2 * n_groups + sizeof(int) * n_fits;
+        unsigned long long *d_sched = (unsigned long long *)tmp_alloc(sched_bytes);
+        Sched sched;
+        sched.t_start = d_sched; sched.cost = d_sched + n_groups; sched.taken = reinterpret_cast<int *>(d_sched + 2 * (size_t)n_groups);
         CU(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(FitTask) * n_fits, cudaMemcpyHostToDevice, p->stream));
-        CU(cudaMemsetAsync(p->d_queue, 0, sizeof(int), p->stream));
+        CU(cudaMemsetAsync(d_sched, 0, sched_bytes, p->stream));
         CU(cudaMemsetAsync(p->d_flops, 0, sizeof(double), p->stream));
         FitOutputs out;
         out.fold_err = d_err; out.status = d_ints; out.n_selected = d_ints + n_fits; out.n_iter = d_ints + 2 * n_fits;
@@ -518,9 +577,9 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
         const int grid = std::min(p->n_slabs, n_fits);
         CU(cudaEventRecord(p->ev0, p->stream));
         if (p->prior == PAREBEN_GAUSSIAN)
-            CU((p->epis ? launch_fit_ge : launch_fit_gm)(grid, p->threads, p->stream, P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out));
+            CU((p->epis ? launch_fit_ge : launch_fit_gm)(grid, p->threads, p->stream, P, v, d_tasks, n_fits, sched, p->d_slabs, p->slab_stride, out));
         else
-            CU((p->epis ? launch_fit_be : launch_fit_bm)(grid, p->threads, p->stream, P, v, d_tasks, n_fits, p->d_queue, p->d_slabs, p->slab_stride, out));
+            CU((p->epis ? launch_fit_be : launch_fit_bm)(grid, p->threads, p->stream, P, v, d_tasks, n_fits, sched, p->d_slabs, p->slab_stride, out));
         CU(cudaEventRecord(p->ev1, p->stream));
         std::vector<int> h_ints(3 * (size_t)n_fits);
         std::vector<double> h_err(n_fits);
@@ -581,19 +640,17 @@ extern "C" int pareben_shard_plan(const double *lambda, int n_grid, int n_folds,
     return PAREBEN_OK;
 }
 
-extern "C" int pareben_cv_grid(const double *basis, int n, int k, const double *target, const int *fold_id,
-                               int n_folds, const double *alpha, const double *lambda, int n_grid, int epis,
-                               int prior, int device, int shard, int n_shards, double *fold_err,
-                               int *status, int *n_selected)
+namespace {
+
+// One sub-shard of a grid call on one device: upload, lay out, run, scatter into the caller's tables.
+int cv_grid_on_device(const double *basis, int n, int k, const double *target, const int *fold_id, int n_folds,
+                      const double *alpha, const double *lambda, int n_grid, int epis, int prior, int device,
+                      int shard, int n_shards, double *fold_err, int *status, int *n_selected)
 {
-    if (n_folds < 1 || n_grid < 1 || !alpha || !lambda || !fold_err) return fail(PAREBEN_EINVAL, "pareben_cv_grid: bad argument");
-    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(PAREBEN_EINVAL, "pareben_cv_grid: bad shard");
     const int total = n_grid * n_folds;
     std::vector<int> mine(total);
-    int m_count = 0;
-    pareben_shard_plan(lambda, n_grid, n_folds, shard, n_shards, mine.data(), &m_count);
-    mine.resize(m_count);
-    const int m = (int)mine.size();
+    int m = 0;
+    pareben_shard_plan(lambda, n_grid, n_folds, shard, n_shards, mine.data(), &m);
     if (m == 0) return PAREBEN_OK;
     pareben_problem *p = nullptr;
     const bool timing = getenv("PAREBEN_TIMING") != nullptr;
@@ -614,8 +671,8 @@ extern "C" int pareben_cv_grid(const double *basis, int n, int k, const double *
     if (timing) {
         auto t3 = std::chrono::steady_clock::now();
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "[pareben] cv_grid: create %.2f ms, run_fits %.2f ms (kernel %.2f ms), destroy %.2f ms\n",
-                ms(t0, t1), ms(t1, t2), kernel_ms, ms(t2, t3));
+        fprintf(stderr, "[pareben] cv_grid dev %d: create %.2f ms, run_fits %.2f ms (kernel %.2f ms), destroy %.2f ms\n",
+                device, ms(t0, t1), ms(t1, t2), kernel_ms, ms(t2, t3));
     }
     if (rc != PAREBEN_OK) return rc;
     for (int i = 0; i < m; i++) {
@@ -623,6 +680,41 @@ extern "C" int pareben_cv_grid(const double *basis, int n, int k, const double *
         if (status) status[mine[i]] = st[i];
         if (n_selected) n_selected[mine[i]] = ns[i];
     }
+    return PAREBEN_OK;
+}
+
+}  // namespace
+
+// n_devices GPUs (device, device + 1, ...) share this call's shard: the foreach fan-out of R/CrossValidate.R:66-70
+// over the box's GPUs from ONE call on ONE host thread of the caller.  Each device is driven by its own worker thread
+// (upload, layout kernels, one fit launch, read-back); the workers write disjoint entries of the caller's tables, so
+// the "gather" is the join.  No R API is touched from the workers.
+extern "C" int pareben_cv_grid(const double *basis, int n, int k, const double *target, const int *fold_id,
+                               int n_folds, const double *alpha, const double *lambda, int n_grid, int epis,
+                               int prior, int n_devices, int device, int shard, int n_shards, double *fold_err,
+                               int *status, int *n_selected)
+{
+    if (n_folds < 1 || n_grid < 1 || !alpha || !lambda || !fold_err) return fail(PAREBEN_EINVAL, "pareben_cv_grid: bad argument");
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(PAREBEN_EINVAL, "pareben_cv_grid: bad shard");
+    const int visible = pareben_device_count();
+    if (visible < 1) return fail(PAREBEN_ENODEVICE, "no usable CUDA device");
+    if (n_devices == 0) n_devices = visible - device;                 // 0 = every device from `device` on
+    if (device < 0 || n_devices < 1 || device + n_devices > visible) return fail(PAREBEN_ENODEVICE, "pareben_cv_grid: device range not available");
+    if (n_devices == 1)
+        return cv_grid_on_device(basis, n, k, target, fold_id, n_folds, alpha, lambda, n_grid, epis, prior, device,
+                                 shard, n_shards, fold_err, status, n_selected);
+    std::vector<int> rcs(n_devices, PAREBEN_OK);
+    std::vector<std::string> msgs(n_devices);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n_devices; d++)
+        workers.emplace_back([&, d] {
+            rcs[d] = cv_grid_on_device(basis, n, k, target, fold_id, n_folds, alpha, lambda, n_grid, epis, prior, device + d,
+                                       shard * n_devices + d, n_shards * n_devices, fold_err, status, n_selected);
+            if (rcs[d] != PAREBEN_OK) msgs[d] = g_err;                // g_err is thread-local: carry the text back
+        });
+    for (std::thread &w : workers) w.join();
+    for (int d = 0; d < n_devices; d++)
+        if (rcs[d] != PAREBEN_OK) return fail(rcs[d], "device " + std::to_string(device + d) + ": " + msgs[d]);
     return PAREBEN_OK;
 }
 
@@ -774,8 +866,9 @@ extern "C" int pareben_sl_filter(pareben_problem *p, double tau_main, double tau
     return PAREBEN_OK;
 }
 
-// experiments only (timing build, -DPAREBEN_PHASE_TIMING): cycles per phase summed over blocks and over the
-// four kernel variants; zeros in the normal build.  out: PH_COUNT cycle totals then PH_COUNT call counts.
+// experiments only (timing build, -DPAREBEN_PHASE_TIMING; absent from the product library): cycles per phase summed over
+// blocks and over the four kernel variants.  out: PH_COUNT cycle totals then PH_COUNT call counts.
+#ifdef PAREBEN_PHASE_TIMING
 extern "C" int pareben_phase_cycles(unsigned long long *out, int reset)
 {
     unsigned long long acc[2 * PH_COUNT] = {0}, one[2 * PH_COUNT];
@@ -790,19 +883,15 @@ extern "C" int pareben_phase_cycles(unsigned long long *out, int reset)
 }
 
 // experiments only: per-fit start/end (%globaltimer ns) and block id of the last launch of variant
-// `which` (0 gm, 1 ge, 2 bm, 3 be); returns 0 in the normal build.
+// `which` (0 gm, 1 ge, 2 bm, 3 be).
 extern "C" int pareben_fit_trace(int which, unsigned long long *t0, unsigned long long *t1, int *block, int n)
 {
-#ifdef PAREBEN_PHASE_TIMING
     void (*fn[4])(unsigned long long *, int, unsigned long long *, unsigned long long *, int *, int) = {timing_gm, timing_ge, timing_bm, timing_be};
     if (which < 0 || which > 3) return 0;
     fn[which](nullptr, 0, t0, t1, block, n);
     return n;
-#else
-    (void)which; (void)t0; (void)t1; (void)block; (void)n;
-    return 0;
-#endif
 }
+#endif  // PAREBEN_PHASE_TIMING
 
 extern "C" int pareben_last_counters(pareben_problem *p, double *flops, double *kernel_ms, int *launches)
 {

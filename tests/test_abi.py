@@ -24,7 +24,7 @@ def test_header_symbols_exported(built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/pareben.h but not exported"
     assert sorted(pb._lib.SIGNATURES) == names, "ctypes binding table out of sync with the header"
-    assert pb.load().pareben_version() == 1
+    assert pb.load().pareben_version() == 2
 
 
 def test_cited_reference_lines_in_header():

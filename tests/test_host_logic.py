@@ -40,8 +40,8 @@ def test_summary_and_local_search_against_oracle(monkeypatch):
     g = golden("config1_gaussian.npz")
     X = golden("inputs_bundled.npz")["BASIS"][:50, :100].astype(float)
     y = golden("inputs_bundled.npz")["y"][:50]
-    monkeypatch.setattr(cv, "BuildGrid", lambda *a, **k: {"alpha": g["grid_alpha"], "lambda": g["grid_lambda"]})
-    monkeypatch.setattr(cv, "_grid_errors", lambda *a, **k: (g["fold_err"].copy(), np.zeros((400, 3), np.int32), g["n_selected"]))
+    grid = {"alpha": g["grid_alpha"], "lambda": g["grid_lambda"]}
+    monkeypatch.setattr(cv, "_grid_and_errors", lambda *a, **k: (grid, g["fold_err"].copy(), np.zeros((400, 3), np.int32), g["n_selected"]))
     out = pb.CrossValidate(X, y, 3)
     assert out["alpha.optimal"] == float(g["alpha_optimal"]) and out["lambda.optimal"] == float(g["lambda_optimal"])
     assert np.array_equal(out["Results.Summary"]["MSE"], g["summary_mse"])
@@ -51,6 +51,58 @@ def test_summary_and_local_search_against_oracle(monkeypatch):
     loc = pb.CrossValidate(X, y, 3, search="local")
     assert np.array_equal(loc["CrossValidation"], g["local_cv"]) and np.array_equal(loc["fullCV"], g["local_full"])
     assert loc["alpha.optimal"] == float(g["local_alpha"]) and loc["lambda.optimal"] == float(g["local_lambda"])
+
+
+def test_which_min_skips_na_and_reports_status(monkeypatch):
+    """R's which.min skips NA (np.argmin would return the first NaN); a fit flagged by its status word must not
+    pass silently; an all-NA table stops like the reference's is.na(Mu0) check."""
+    import warnings
+    import pytest
+    import pareben_b200 as pb
+    from pareben_b200 import cross_validate as cv
+    g = golden("config1_gaussian.npz")
+    grid = {"alpha": g["grid_alpha"], "lambda": g["grid_lambda"]}
+    err = g["fold_err"].copy()
+    order = np.lexsort((grid["lambda"], grid["alpha"]))
+    err[order[0], 1] = np.nan                       # first row of the sorted summary becomes NA
+    st = np.zeros((400, 3), np.int32); st[order[0], 1] = pb.FIT_NONFINITE; st[5, 0] = pb.FIT_BASIS_CAP
+    monkeypatch.setattr(cv, "_grid_and_errors", lambda *a, **k: (grid, err.copy(), st, g["n_selected"]))
+    X = np.zeros((50, 100)); y = np.zeros(50)
+    with pytest.warns(RuntimeWarning, match="2 of 1200 fits.*basis cap 1.*non-finite 1"):
+        out = pb.CrossValidate(X, y, 3)
+    assert out["alpha.optimal"] == float(g["alpha_optimal"]) and out["lambda.optimal"] == float(g["lambda_optimal"])
+    assert np.isnan(out["Results.Summary"]["MSE"][0])
+    with pytest.warns(RuntimeWarning):
+        loc = pb.CrossValidate(X, y, 3, search="local")
+    assert np.isfinite(loc["alpha.optimal"])
+    monkeypatch.setattr(cv, "_grid_and_errors", lambda *a, **k: (grid, np.full((400, 3), np.nan), np.zeros((400, 3), np.int32), g["n_selected"]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(ValueError, match="NA"):
+            pb.CrossValidate(X, y, 3)
+
+
+def test_cv_grid_validates_lengths(built):
+    """The C side only sees pointers: mismatched lengths must raise before the ctypes call (no device needed)."""
+    import pytest
+    import pareben_b200 as pb
+    X = np.zeros((10, 3)); y = np.arange(10.0); f = np.tile([1, 2], 5)
+    with pytest.raises(ValueError, match="Target"):
+        pb.cv_grid(X, y[:9], f, 2, np.ones(2), np.ones(2))
+    with pytest.raises(ValueError, match="fold_id"):
+        pb.cv_grid(X, y, f[:8], 2, np.ones(2), np.ones(2))
+    with pytest.raises(ValueError, match="alpha"):
+        pb.cv_grid(X, y, f, 2, np.ones(3), np.ones(2))
+    with pytest.raises(ValueError, match="n_folds"):
+        pb.cv_grid(X, y, f, 0, np.ones(2), np.ones(2))
+
+
+def test_default_device_follows_local_rank(monkeypatch):
+    import pareben_b200 as pb
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    assert pb.default_device() == 0
+    monkeypatch.setenv("LOCAL_RANK", "3")
+    assert pb.default_device() == 3
 
 
 def test_two_rank_gloo_merge(tmp_path):
@@ -67,13 +119,19 @@ def test_two_rank_gloo_merge(tmp_path):
         rank, world = dist.get_rank(), dist.get_world_size()
         lam = np.repeat(np.exp(np.linspace(1, -6, 20)), 20); alpha = np.tile(np.linspace(1, .05, 20), 20)
         truth = np.sin(np.arange(1200.0)).reshape(400, 3) + 3
-        def fake(X, y, f, nf, a, l, epis, prior, device, shard=0, n_shards=1):
-            mine = pb.shard_plan(l, nf, shard, n_shards)
-            err = np.zeros(1200); st = np.zeros(1200, np.int32); ns = np.zeros(1200, np.int32)
-            err[mine] = truth.ravel()[mine]; ns[mine] = mine % 7; st[mine] = (mine % 11 == 0)
-            return err.reshape(400, 3), st.reshape(400, 3), ns.reshape(400, 3)
-        _lib.cv_grid = fake
-        err, st, ns = cv._grid_errors(None, None, None, 3, alpha, lam, False, "gaussian", 0)
+        class FakeProblem:                    # stands where the device-resident problem would be: fills only this rank's shard
+            def __init__(self, *a, **k): pass
+            def __enter__(self): return self
+            def __exit__(self, *e): pass
+            def lambda_max(self): return 1.0
+            def cv_grid(self, a, l, shard=0, n_shards=1):
+                mine = pb.shard_plan(l, 3, shard, n_shards)
+                err = np.zeros(1200); st = np.zeros(1200, np.int32); ns = np.zeros(1200, np.int32)
+                err[mine] = truth.ravel()[mine]; ns[mine] = mine % 7; st[mine] = (mine % 11 == 0)
+                return err.reshape(400, 3), st.reshape(400, 3), ns.reshape(400, 3)
+        _lib.Problem = FakeProblem
+        cv._grid_from_lambda_max = lambda lm: {{"alpha": alpha, "lambda": lam}}
+        grid, err, st, ns = cv._grid_and_errors(None, None, None, 3, "no", "gaussian", 0)
         assert np.array_equal(err, truth), "merged table differs"
         assert np.array_equal(ns.ravel(), np.arange(1200) % 7) and np.array_equal(st.ravel(), (np.arange(1200) % 11 == 0).astype(np.int32))
         dist.destroy_process_group()
