@@ -207,3 +207,35 @@ def test_binomial_final_model_live(pb, bundled):
         assert np.allclose(got["weight"][:, 2:4], want.weight[:, 2:4], rtol=1e-7, atol=1e-12)
         assert np.allclose(got["Intercept"], want.intercept, rtol=1e-7)
         assert abs(got["logLikelihood"] - want.log_likelihood) <= 1e-8 * abs(want.log_likelihood)
+
+
+def test_one_call_over_two_devices(pb, bundled):
+    """pareben_cv_grid(n_devices = 2): one call, two GPUs, in-library gather -- bitwise the single-GPU table."""
+    if pb.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = golden("config2_binomial.npz")
+    X, y = bundled["BASISbinomial"].astype(float), bundled["yBinomial"].astype(float)
+    rows = np.arange(0, 400, 3)
+    a, l = g["grid_alpha"][rows], g["grid_lambda"][rows]
+    e1, s1, n1 = pb.cv_grid(X, y, g["fold_id"], 5, a, l, prior="binomial")
+    e2, s2, n2 = pb.cv_grid(X, y, g["fold_id"], 5, a, l, prior="binomial", n_devices=2)
+    e0, s0, n0 = pb.cv_grid(X, y, g["fold_id"], 5, a, l, prior="binomial", n_devices=0)       # 0 = every visible device
+    assert np.array_equal(e1, e2) and np.array_equal(s1, s2) and np.array_equal(n1, n2)
+    assert np.array_equal(e1, e0)
+    with pytest.raises(pb.ParebenError):
+        pb.cv_grid(X, y, g["fold_id"], 5, a, l, prior="binomial", n_devices=pb.device_count() + 1)
+
+
+def test_cross_validate_end_to_end_single_upload(pb, bundled):
+    """CrossValidate through the public mirror: BuildGrid's lambda_max and the fits share one resident problem; the result
+    equals the golden table made from the reference's C (config 1)."""
+    g = golden("config1_gaussian.npz")
+    X, y = bundled["BASIS"][:50, :100].astype(float), bundled["y"][:50]
+    out = pb.CrossValidate(X, y, 3)
+    assert out["alpha.optimal"] == float(g["alpha_optimal"])
+    assert abs(out["lambda.optimal"] - float(g["lambda_optimal"])) <= 1e-12 * float(g["lambda_optimal"])   # lambda_max is summed on the device
+    assert np.allclose(out["Results.Summary"]["MSE"], g["summary_mse"], rtol=RTOL, atol=0)
+    assert np.allclose(out["Results.Summary"]["lambda"], np.sort(np.unique(g["grid_lambda"]))[np.tile(np.arange(20), 20)], rtol=1e-12, atol=0)
+    if pb.device_count() >= 2:
+        out2 = pb.CrossValidate(X, y, 3, n_devices=2)
+        assert np.array_equal(out2["Results.Detail"]["MSE"], out["Results.Detail"]["MSE"])
