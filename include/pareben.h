@@ -46,6 +46,7 @@ extern "C" {
 #define PAREBEN_FIT_NOT_PD      2   /* a Hessian was not positive definite */
 #define PAREBEN_FIT_NONFINITE   4   /* non-finite hold-out error */
 #define PAREBEN_FIT_ITER_MAX    8   /* outer loop hit its 100-iteration limit */
+#define PAREBEN_FIT_LIST_CAP   16   /* streaming mode: more than 4096 candidates tied within n_add of the best addition */
 
 typedef struct pareben_problem pareben_problem;
 
@@ -127,6 +128,18 @@ int pareben_sl_filter(pareben_problem *p, double tau_main, double tau_pair, int 
  * (SURVEY.md 8d): algorithmic FP64 flops of the contraction/statistics phases, kernel
  * milliseconds measured with CUDA events on the launch stream, launches issued. */
 int pareben_last_counters(pareben_problem *p, double *flops, double *kernel_ms, int *launches);
+
+/* Solver organisation.  mode 0 (default) = automatic, 1 = cached kernel, 2 = streaming kernels.
+ * The cached kernel keeps the reference's per-fit candidate cache (BASIS_PHI, one row of Kc doubles per active basis,
+ * NeFull2.c:350-365) in device memory; the streaming kernels keep only the active set and recompute the per-candidate
+ * statistics by one dense contraction per fold for all fits at once -- the only form that exists at
+ * Kc = k(k+1)/2 = 2e8 (BASELINE config 5), where the reference itself cannot allocate.  Automatic = streaming above
+ * 4,000,000 candidates (PAREBEN_STREAM_KC), Gaussian prior only.  The setting is read by pareben_problem_create. */
+int pareben_set_mode(int mode);
+int pareben_is_streaming(pareben_problem *p);
+/* Streaming mode's share of the last pareben_run_fits: summed CUDA-event time and algorithmic flops
+ * (2 x training rows x candidates per waiting fit) of the score-contraction launches, their number, and the rounds. */
+int pareben_last_stream_counters(pareben_problem *p, double *scan_ms, double *scan_flops, int *scan_launches, int *rounds);
 
 /* FP64 peak probes for the roofline denominator (MEASURED_PEAKS.json carries no FP64 figure):
  * which = 0 -> DFMA chains on the CUDA cores, 1 -> DMMA (mma.sync.m8n8k4.f64). */

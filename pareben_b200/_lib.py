@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PAREBEN_LIB") or os.path.join(_HERE, "libpareben.so")
 
 GAUSSIAN, BINOMIAL = 0, 1
-FIT_BASIS_CAP, FIT_NOT_PD, FIT_NONFINITE, FIT_ITER_MAX = 1, 2, 4, 8
+FIT_BASIS_CAP, FIT_NOT_PD, FIT_NONFINITE, FIT_ITER_MAX, FIT_LIST_CAP = 1, 2, 4, 8, 16
+MODE_AUTO, MODE_CACHED, MODE_STREAMING = 0, 1, 2
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
@@ -35,6 +36,9 @@ SIGNATURES = {
     "pareben_lambda_max": (ctypes.c_int, [_vp, _dp]),
     "pareben_sl_filter": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, _ip, _dp, _ip]),
     "pareben_last_counters": (ctypes.c_int, [_vp, _dp, _dp, _ip]),
+    "pareben_set_mode": (ctypes.c_int, [ctypes.c_int]),
+    "pareben_is_streaming": (ctypes.c_int, [_vp]),
+    "pareben_last_stream_counters": (ctypes.c_int, [_vp, _dp, _dp, _ip, _ip]),
     "pareben_measure_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _dp]),
     "pareben_device_count": (ctypes.c_int, []),
     "pareben_last_error": (ctypes.c_char_p, []),
@@ -84,6 +88,11 @@ def device_count() -> int:
 def release_cache() -> None:
     """Give the library's idle device buffers back to the driver (pareben_release_cache)."""
     load().pareben_release_cache()
+
+
+def set_mode(mode: int) -> None:
+    """pareben_set_mode: 0 automatic, 1 cached kernel, 2 streaming kernels (read when a problem is created)."""
+    _check(load().pareben_set_mode(int(mode)))
 
 
 def default_device() -> int:
@@ -181,6 +190,16 @@ class Problem:
             if cnt.value <= cap:
                 return cand[:cnt.value].copy(), stat[:cnt.value].copy()
             cap = cnt.value
+
+    @property
+    def streaming(self) -> bool:
+        return bool(load().pareben_is_streaming(self._h))
+
+    def stream_counters(self):
+        """(scan ms, scan flops, scan launches, rounds) of the last run_fits in streaming mode."""
+        ms = np.zeros(1); fl = np.zeros(1); ln = np.zeros(1, np.int32); rd = np.zeros(1, np.int32)
+        _check(load().pareben_last_stream_counters(self._h, _d(ms), _d(fl), _i(ln), _i(rd)))
+        return float(ms[0]), float(fl[0]), int(ln[0]), int(rd[0])
 
     def counters(self):
         fl = np.zeros(1); ms = np.zeros(1); ln = np.zeros(1, np.int32)

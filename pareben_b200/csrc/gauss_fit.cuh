@@ -982,7 +982,10 @@ __device__ inline bool spd_inverse_sweep(double *a, int M, double *colk, const S
     if (sm && M <= SWEEP_SMEM_M && T == 256) {
         ok = M <= 32 ? sweep_regs<1>(a, M, sm) : sweep_regs<2>(a, M, sm);
     } else {
-        ok = sm ? sweep_panel(a, M, sm) : sweep_core(a, M, colk);          // colk: 2*(cap+1) doubles in the slab
+        // the panel arrays need 3 * 4 * (M rounded up to 8, + 4) doubles even at the narrowest panel: beyond that
+        // (M > 420) the one-pivot sweep in global memory takes over
+        const bool panel_fits = 12 * (((M + 7) & ~7) + 4) + 8 <= SWEEP_PANEL_DOUBLES;
+        ok = (sm && panel_fits) ? sweep_panel(a, M, sm) : sweep_core(a, M, colk);          // colk: 2*(cap+1) doubles in the slab
         if (ok) for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -a[idx];
     }
     __syncthreads();

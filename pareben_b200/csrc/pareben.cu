@@ -6,6 +6,7 @@
 #include "../../include/pareben.h"
 #include "common.cuh"
 #include "fit_launch.h"
+#include "stream_launch.h"
 
 #include <algorithm>
 #include <map>
@@ -25,6 +26,21 @@ namespace {
 thread_local std::string g_err;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+// 0 = auto, 1 = cached kernel (fit_kernel.cuh), 2 = streaming kernels (stream.cuh)
+int g_mode = 0;
+
+// Streaming mode is for candidate sets whose per-fit cache cannot exist (config 5: Kc = 2e8).  Auto: above
+// PAREBEN_STREAM_KC candidates (default 4,000,000: at 64 active bases the cache alone would be 2 GB per resident fit).
+bool want_streaming(int kc, int prior)
+{
+    if (prior != PAREBEN_GAUSSIAN) return false;          // the binomial solver has no streaming form yet
+    if (g_mode == 1) return false;
+    if (g_mode == 2) return true;
+    const char *e = getenv("PAREBEN_STREAM_KC");
+    const long long lim = e ? atoll(e) : 4000000LL;
+    return (long long)kc > lim;
+}
 
 // Per-device pool of device allocations.  cudaMalloc/cudaFree synchronise the device and can
 // take hundreds of milliseconds for multi-GB buffers, which would dominate a CrossValidate call
@@ -274,6 +290,8 @@ struct pareben_problem {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int threads = 256;                   // threads per block actually launched
     double last_flops = 0, last_ms = 0; int last_launches = 0;
+    bool streaming = false;              // fits run through the streaming kernels (no per-candidate arrays anywhere)
+    double last_scan_ms = 0, last_scan_flops = 0; int last_scan_launches = 0, last_rounds = 0;
 
     template <class T> T *dalloc(size_t n)
     {
@@ -402,6 +420,8 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         };
         p->n = n; p->k = k; p->epis = epis; p->prior = prior; p->n_folds = n_folds;
         p->kc = epis ? (int)((long long)k * (k + 1) / 2) : k;
+        p->streaming = want_streaming(p->kc, prior);
+        if (p->streaming && n_folds + 1 > STREAM_MAX_FOLDS) throw std::make_pair((int)PAREBEN_EINVAL, std::string("streaming mode supports at most 255 folds"));
         CU(cudaStreamCreate(&p->stream));
         CU(cudaEventCreate(&p->ev0)); CU(cudaEventCreate(&p->ev1));
 
@@ -444,7 +464,7 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
             CU(cudaStreamSynchronize(p->stream));      // tr/te go out of scope
             double *Xtr = p->dalloc<double>((size_t)F.ntr * k), *ytr = p->dalloc<double>(F.ntr);
             double *Xte = p->dalloc<double>((size_t)F.nte * k), *yte = p->dalloc<double>(F.nte);
-            double *scale = p->dalloc<double>(p->kc);
+            double *scale = p->streaming ? nullptr : p->dalloc<double>(p->kc);     // streaming: norms are computed on the fly
             dim3 blk(32, 8);
             gather_rows_kernel<<<dim3((F.ntr + 31) / 32, (k + 31) / 32), blk, 0, p->stream>>>(p->d_Xcol, n, k, d_rows, F.ntr, Xtr);
             gather_vec_kernel<<<(F.ntr + 255) / 256, 256, 0, p->stream>>>(p->d_y, d_rows, F.ntr, ytr);
@@ -452,8 +472,10 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
                 gather_rows_kernel<<<dim3((F.nte + 31) / 32, (k + 31) / 32), blk, 0, p->stream>>>(p->d_Xcol, n, k, d_rows + F.ntr, F.nte, Xte);
                 gather_vec_kernel<<<(F.nte + 255) / 256, 256, 0, p->stream>>>(p->d_y, d_rows + F.ntr, F.nte, yte);
             }
-            if (epis) scales_kernel<true><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
-            else scales_kernel<false><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
+            if (scale) {
+                if (epis) scales_kernel<true><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
+                else scales_kernel<false><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
+            }
             F.Xtr = Xtr; F.ytr = ytr; F.Xte = Xte; F.yte = yte; F.scale = scale; F.Xtr8 = nullptr;
             F.XT8 = nullptr; F.XTd = nullptr;
             F.ldt = (F.ntr + 63) & ~63;      // whole stages of the contraction (KT = 64 rows)
@@ -510,11 +532,175 @@ namespace {
 
 struct DumpBuffers { int *m = nullptr, *used = nullptr; double *beta = nullptr, *var = nullptr, *scalars = nullptr; };
 
+// Streaming mode (stream.cuh): every fit keeps only its active set; all fits advance in lock-step rounds of
+//   stream_advance_kernel (one block per fit)  ->  stream_scan_kernel (one dense contraction per fold for all waiting fits)
+// until no fit is waiting for a scan.  One 4-byte-per-fold read-back per round tells the host when to stop.
+int run_fits_streaming(pareben_problem *p, int n_fits, const int *fold, const double *alpha, const double *lambda,
+                       double *fold_err, int *status, int *n_selected, int *n_iter, DumpBuffers *dump)
+{
+    std::vector<std::pair<void *, size_t>> scratch;
+    cudaEvent_t es0 = nullptr, es1 = nullptr;
+    try {
+        CU(cudaSetDevice(p->device));
+        const int nf1 = p->n_folds + 1;
+        auto tmp_alloc = [&](size_t bytes) {
+            bytes = (std::max<size_t>(bytes, 8) + 255) & ~(size_t)255;
+            void *q = pool_take(p->device, bytes, false, nullptr);
+            if (!q) CU(malloc_retry(p->device, &q, bytes));
+            scratch.emplace_back(q, bytes); return q; };
+        // basis cap: the reference's basisMax, bounded by PAREBEN_BASIS_CAP and by what n_fits active sets may occupy
+        int cap = reference_basis_max(p->min_ntr, p->k, p->kc, p->epis, p->prior);
+        const char *env_cap = getenv("PAREBEN_BASIS_CAP");
+        cap = std::max(2, std::min(cap, env_cap ? atoi(env_cap) : 1024));
+        const int list_cap = 4096;
+        const int LD = phi_ld(p->nmax);
+        auto fit_doubles = [&](int c) { return (size_t)4 * c * c + (size_t)LD * c + (size_t)12 * (c + 1) + (size_t)4 * p->nmax + (size_t)2 * list_cap + 16; };
+        auto fit_ints = [&](int c) { return (size_t)2 * c + (size_t)4 * (c + list_cap) + list_cap + 16; };
+        auto fit_bytes = [&](int c) { return ((fit_doubles(c) * 8 + fit_ints(c) * 4) + 255) & ~(size_t)255; };
+        {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            free_b += pool_parked(p->device);
+            while (cap > 16 && fit_bytes(cap) * (size_t)n_fits > free_b / 2) cap = cap * 3 / 4;
+        }
+        p->cap = cap;
+        const size_t stride = fit_bytes(cap);
+        char *d_state = (char *)tmp_alloc(stride * (size_t)n_fits);
+        StreamFit *d_fits = (StreamFit *)tmp_alloc(sizeof(StreamFit) * (size_t)n_fits);
+        std::vector<StreamFit> h_fits(n_fits);
+        std::vector<int> per_fold(nf1, 0);
+        for (int i = 0; i < n_fits; i++) {
+            if (fold[i] < 0 || fold[i] > p->n_folds || (p->n_folds > 0 && fold[i] == 0) || !p->h_folds[fold[i]].Xtr)
+                return fail(PAREBEN_EINVAL, "pareben_run_fits: fold label not available in this problem");
+            per_fold[fold[i]]++;
+            StreamFit f;
+            memset(&f, 0, sizeof f);
+            f.fold = fold[i]; f.out_index = i; f.lambda = lambda[i]; f.alpha_en = alpha[i]; f.phase = SP_START;
+            double *d = reinterpret_cast<double *>(d_state + stride * (size_t)i);
+            const size_t cc = (size_t)cap * cap;
+            f.sigma = d; d += cc; f.sigma_new = d; d += cc; f.H = d; d += cc; f.ptp = d; d += cc;
+            f.phi = d; d += (size_t)LD * cap;
+            f.mu = d; d += cap + 1; f.alpha = d; d += cap + 1; f.gamma = d; d += cap + 1; f.tmp = d; d += cap + 1; f.u = d; d += cap + 1;
+            f.colk = d; d += 2 * (cap + 1); f.ascale = d; d += cap + 1; f.s_in = d; d += cap + 1; f.q_in = d; d += cap + 1;
+            f.dml_in = d; d += cap + 1; f.aroot_in = d; d += cap + 1;
+            f.t = d; d += p->nmax; f.e = d; d += p->nmax; f.d = d; d += p->nmax; f.phinew = d; d += p->nmax;
+            f.list_dml = d; d += list_cap; f.list_aroot = d; d += list_cap;
+            int *ip = reinterpret_cast<int *>(d);
+            f.used = ip; ip += cap; f.act_in = ip; ip += cap;
+            f.blk_c = ip; ip += 2 * (cap + list_cap); f.blk_src = ip; ip += 2 * (cap + list_cap);
+            f.list_c = ip; ip += list_cap;
+            h_fits[i] = f;
+        }
+        CU(cudaMemcpyAsync(d_fits, h_fits.data(), sizeof(StreamFit) * (size_t)n_fits, cudaMemcpyHostToDevice, p->stream));
+        // per-fold round buffers
+        std::vector<StreamFold> h_sf(nf1);
+        for (int f = 0; f < nf1; f++) {
+            StreamFold sf; memset(&sf, 0, sizeof sf);
+            if (per_fold[f] > 0) {
+                const int n_rt = (per_fold[f] + SN - 1) / SN;
+                sf.max_slots = n_rt * SN;
+                sf.E = (double *)tmp_alloc(sizeof(double) * e_tile_doubles(p->h_folds[f].ldt) * n_rt);
+                CU(cudaMemsetAsync(sf.E, 0, sizeof(double) * e_tile_doubles(p->h_folds[f].ldt) * n_rt, p->stream));
+                sf.thr = (double *)tmp_alloc(sizeof(double) * sf.max_slots);
+                sf.slot_fit = (int *)tmp_alloc(sizeof(int) * sf.max_slots);
+            }
+            h_sf[f] = sf;
+        }
+        StreamFold *d_sf = (StreamFold *)tmp_alloc(sizeof(StreamFold) * nf1);
+        CU(cudaMemcpyAsync(d_sf, h_sf.data(), sizeof(StreamFold) * nf1, cudaMemcpyHostToDevice, p->stream));
+        int *d_nslots = (int *)tmp_alloc(sizeof(int) * nf1);
+        const int scan_grid = p->sm_count;
+        double *d_wscratch = (double *)tmp_alloc(sizeof(double) * (size_t)scan_grid * SCAN_WARPS * cap);
+        double *d_err = (double *)tmp_alloc(sizeof(double) * n_fits);
+        int *d_ints = (int *)tmp_alloc(sizeof(int) * 3 * n_fits);
+        CU(cudaMemsetAsync(p->d_flops, 0, sizeof(double), p->stream));
+        CU(cudaMemsetAsync(d_nslots, 0, sizeof(int) * nf1, p->stream));
+        StreamShared sh;
+        sh.folds = d_sf; sh.n_slots = d_nslots; sh.list_cap = list_cap; sh.warp_scratch = d_wscratch; sh.flops = p->d_flops;
+        FitOutputs out;
+        out.fold_err = d_err; out.status = d_ints; out.n_selected = d_ints + n_fits; out.n_iter = d_ints + 2 * n_fits;
+        out.m_out = nullptr; out.used_out = nullptr; out.beta_out = nullptr; out.var_out = nullptr; out.scalars_out = nullptr;
+        out.flops = p->d_flops;
+        if (dump) {
+            dump->m = (int *)tmp_alloc(sizeof(int) * (1 + cap));
+            dump->used = dump->m + 1;
+            dump->beta = (double *)tmp_alloc(sizeof(double) * (2 * cap + 4));
+            dump->var = dump->beta + cap; dump->scalars = dump->var + cap;
+            out.m_out = dump->m; out.used_out = dump->used; out.beta_out = dump->beta; out.var_out = dump->var; out.scalars_out = dump->scalars;
+        }
+        Problem P;
+        P.N = p->n; P.K = p->k; P.Kc = p->kc; P.n_folds = p->n_folds; P.epis = p->epis; P.prior = p->prior;
+        P.cap = cap; P.nmax = p->nmax; P.folds = p->d_folds;
+        const Variant v = make_variant(p->epis, p->prior);
+        auto advance = [&] { CU((p->epis ? launch_stream_advance_ge : launch_stream_advance_gm)(n_fits, p->stream, P, v, d_fits, sh, out)); };
+        auto scan = [&] { CU((p->epis ? launch_stream_scan_ge : launch_stream_scan_gm)(scan_grid, p->stream, P, d_fits, sh)); };
+        CU(cudaEventCreate(&es0)); CU(cudaEventCreate(&es1));
+        std::vector<int> h_nslots(nf1);
+        double scan_ms = 0, scan_flops = 0;
+        int rounds = 0, scans = 0;
+        const bool timing = getenv("PAREBEN_TIMING") != nullptr;
+        CU(cudaEventRecord(p->ev0, p->stream));
+        advance();
+        for (;;) {
+            CU(cudaMemcpyAsync(h_nslots.data(), d_nslots, sizeof(int) * nf1, cudaMemcpyDeviceToHost, p->stream));
+            CU(cudaStreamSynchronize(p->stream));
+            if (scans > 0) { float ms = 0; CU(cudaEventElapsedTime(&ms, es0, es1)); scan_ms += ms; }
+            long long waiting = 0;
+            double fl = 0;
+            for (int f = 0; f < nf1; f++) { waiting += h_nslots[f]; fl += 2.0 * p->h_folds[f].ntr * (double)p->kc * h_nslots[f]; }
+            if (timing) fprintf(stderr, "[pareben] stream round %d: %lld fits waiting\n", rounds, waiting);
+            if (waiting == 0) break;
+            scan_flops += fl;
+            CU(cudaEventRecord(es0, p->stream));
+            scan();
+            CU(cudaEventRecord(es1, p->stream));
+            scans++;
+            CU(cudaMemsetAsync(d_nslots, 0, sizeof(int) * nf1, p->stream));
+            advance();
+            rounds++;
+        }
+        CU(cudaEventRecord(p->ev1, p->stream));
+        std::vector<int> h_ints(3 * (size_t)n_fits);
+        std::vector<double> h_err(n_fits);
+        CU(cudaMemcpyAsync(h_err.data(), d_err, sizeof(double) * n_fits, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaMemcpyAsync(h_ints.data(), d_ints, sizeof(int) * 3 * n_fits, cudaMemcpyDeviceToHost, p->stream));
+        double h_flops = 0;
+        CU(cudaMemcpyAsync(&h_flops, p->d_flops, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+        p->last_ms = ms; p->last_flops = h_flops; p->last_launches = 1 + scans + rounds;
+        p->last_scan_ms = scan_ms; p->last_scan_flops = scan_flops; p->last_scan_launches = scans; p->last_rounds = rounds;
+        for (int i = 0; i < n_fits; i++) {
+            if (fold_err) fold_err[i] = h_err[i];
+            if (status) status[i] = h_ints[i];
+            if (n_selected) n_selected[i] = h_ints[n_fits + i];
+            if (n_iter) n_iter[i] = h_ints[2 * (size_t)n_fits + i];
+        }
+        if (dump) {
+            int *hm = (int *)malloc(sizeof(int) * (1 + cap));
+            double *hb = (double *)malloc(sizeof(double) * (2 * cap + 4));
+            CU(cudaMemcpy(hm, dump->m, sizeof(int) * (1 + cap), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(hb, dump->beta, sizeof(double) * (2 * cap + 4), cudaMemcpyDeviceToHost));
+            dump->m = hm; dump->used = hm + 1; dump->beta = hb; dump->var = hb + cap; dump->scalars = hb + 2 * cap;
+        }
+        cudaEventDestroy(es0); cudaEventDestroy(es1);
+        for (auto &q : scratch) pool_give(p->device, q.first, q.second);
+    } catch (std::pair<int, std::string> &e) {
+        if (es0) cudaEventDestroy(es0);
+        if (es1) cudaEventDestroy(es1);
+        for (auto &q : scratch) pool_give(p->device, q.first, q.second);
+        return fail(e.first, e.second);
+    }
+    return PAREBEN_OK;
+}
+
 int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double *alpha, const double *lambda,
                   double *fold_err, int *status, int *n_selected, int *n_iter, DumpBuffers *dump)
 {
     if (!p || n_fits < 0 || (n_fits > 0 && (!fold || !alpha || !lambda))) return fail(PAREBEN_EINVAL, "pareben_run_fits: bad argument");
     if (n_fits == 0) return PAREBEN_OK;
+    if (p->streaming) return run_fits_streaming(p, n_fits, fold, alpha, lambda, fold_err, status, n_selected, n_iter, dump);
     void *scratch[8] = {nullptr};
     size_t scratch_bytes[8] = {0};
     int ns = 0;
@@ -892,6 +1078,25 @@ extern "C" int pareben_fit_trace(int which, unsigned long long *t0, unsigned lon
     return n;
 }
 #endif  // PAREBEN_PHASE_TIMING
+
+extern "C" int pareben_set_mode(int mode)
+{
+    if (mode < 0 || mode > 2) return fail(PAREBEN_EINVAL, "pareben_set_mode: mode must be 0 (auto), 1 (cached) or 2 (streaming)");
+    g_mode = mode;
+    return PAREBEN_OK;
+}
+
+extern "C" int pareben_is_streaming(pareben_problem *p) { return p && p->streaming ? 1 : 0; }
+
+extern "C" int pareben_last_stream_counters(pareben_problem *p, double *scan_ms, double *scan_flops, int *scan_launches, int *rounds)
+{
+    if (!p) return fail(PAREBEN_EINVAL, "null problem");
+    if (scan_ms) *scan_ms = p->last_scan_ms;
+    if (scan_flops) *scan_flops = p->last_scan_flops;
+    if (scan_launches) *scan_launches = p->last_scan_launches;
+    if (rounds) *rounds = p->last_rounds;
+    return PAREBEN_OK;
+}
 
 extern "C" int pareben_last_counters(pareben_problem *p, double *flops, double *kernel_ms, int *launches)
 {
