@@ -592,31 +592,34 @@ int run_fits_streaming(pareben_problem *p, int n_fits, const int *fold, const do
             h_fits[i] = f;
         }
         CU(cudaMemcpyAsync(d_fits, h_fits.data(), sizeof(StreamFit) * (size_t)n_fits, cudaMemcpyHostToDevice, p->stream));
-        // per-fold round buffers
-        std::vector<StreamFold> h_sf(nf1);
-        for (int f = 0; f < nf1; f++) {
+        // per-(fold, class) round buffers: index STREAM_CLASSES * f + cls (stream.cuh)
+        const int nvf = STREAM_CLASSES * nf1;
+        std::vector<StreamFold> h_sf(nvf);
+        for (int vf = 0; vf < nvf; vf++) {
             StreamFold sf; memset(&sf, 0, sizeof sf);
+            const int f = vf / STREAM_CLASSES, cls = vf % STREAM_CLASSES;
             if (per_fold[f] > 0) {
-                const int n_rt = (per_fold[f] + SN - 1) / SN;
+                const int per = class_fits_per_tile(cls);
+                const int n_rt = (per_fold[f] + per - 1) / per;
                 sf.max_slots = n_rt * SN;
                 sf.E = (double *)tmp_alloc(sizeof(double) * e_tile_doubles(p->h_folds[f].ldt) * n_rt);
                 CU(cudaMemsetAsync(sf.E, 0, sizeof(double) * e_tile_doubles(p->h_folds[f].ldt) * n_rt, p->stream));
-                sf.thr = (double *)tmp_alloc(sizeof(double) * sf.max_slots);
+                sf.par = (ScanSlot *)tmp_alloc(sizeof(ScanSlot) * sf.max_slots);
                 sf.slot_fit = (int *)tmp_alloc(sizeof(int) * sf.max_slots);
             }
-            h_sf[f] = sf;
+            h_sf[vf] = sf;
         }
-        StreamFold *d_sf = (StreamFold *)tmp_alloc(sizeof(StreamFold) * nf1);
-        CU(cudaMemcpyAsync(d_sf, h_sf.data(), sizeof(StreamFold) * nf1, cudaMemcpyHostToDevice, p->stream));
-        int *d_nslots = (int *)tmp_alloc(sizeof(int) * nf1);
+        StreamFold *d_sf = (StreamFold *)tmp_alloc(sizeof(StreamFold) * nvf);
+        CU(cudaMemcpyAsync(d_sf, h_sf.data(), sizeof(StreamFold) * nvf, cudaMemcpyHostToDevice, p->stream));
+        int *d_nslots = (int *)tmp_alloc(sizeof(int) * nvf);
         const int scan_grid = p->sm_count;
         double *d_wscratch = (double *)tmp_alloc(sizeof(double) * (size_t)scan_grid * SCAN_WARPS * cap);
         double *d_err = (double *)tmp_alloc(sizeof(double) * n_fits);
         int *d_ints = (int *)tmp_alloc(sizeof(int) * 3 * n_fits);
         CU(cudaMemsetAsync(p->d_flops, 0, sizeof(double), p->stream));
-        CU(cudaMemsetAsync(d_nslots, 0, sizeof(int) * nf1, p->stream));
+        CU(cudaMemsetAsync(d_nslots, 0, sizeof(int) * nvf, p->stream));
         StreamShared sh;
-        sh.folds = d_sf; sh.n_slots = d_nslots; sh.list_cap = list_cap; sh.warp_scratch = d_wscratch; sh.flops = p->d_flops;
+        sh.folds = d_sf; sh.n_slots = d_nslots; sh.list_cap = list_cap; { const char *w = getenv("PAREBEN_STREAM_WIDE"); sh.wide = w ? atoi(w) : 0; } sh.warp_scratch = d_wscratch; sh.flops = p->d_flops;
         FitOutputs out;
         out.fold_err = d_err; out.status = d_ints; out.n_selected = d_ints + n_fits; out.n_iter = d_ints + 2 * n_fits;
         out.m_out = nullptr; out.used_out = nullptr; out.beta_out = nullptr; out.var_out = nullptr; out.scalars_out = nullptr;
@@ -635,27 +638,29 @@ int run_fits_streaming(pareben_problem *p, int n_fits, const int *fold, const do
         auto advance = [&] { CU((p->epis ? launch_stream_advance_ge : launch_stream_advance_gm)(n_fits, p->stream, P, v, d_fits, sh, out)); };
         auto scan = [&] { CU((p->epis ? launch_stream_scan_ge : launch_stream_scan_gm)(scan_grid, p->stream, P, d_fits, sh)); };
         CU(cudaEventCreate(&es0)); CU(cudaEventCreate(&es1));
-        std::vector<int> h_nslots(nf1);
+        std::vector<int> h_nslots(nvf);
         double scan_ms = 0, scan_flops = 0;
         int rounds = 0, scans = 0;
         const bool timing = getenv("PAREBEN_TIMING") != nullptr;
         CU(cudaEventRecord(p->ev0, p->stream));
         advance();
         for (;;) {
-            CU(cudaMemcpyAsync(h_nslots.data(), d_nslots, sizeof(int) * nf1, cudaMemcpyDeviceToHost, p->stream));
+            CU(cudaMemcpyAsync(h_nslots.data(), d_nslots, sizeof(int) * nvf, cudaMemcpyDeviceToHost, p->stream));
             CU(cudaStreamSynchronize(p->stream));
-            if (scans > 0) { float ms = 0; CU(cudaEventElapsedTime(&ms, es0, es1)); scan_ms += ms; }
+            float last_scan_ms = 0;
+            if (scans > 0) { CU(cudaEventElapsedTime(&last_scan_ms, es0, es1)); scan_ms += last_scan_ms; }
             long long waiting = 0;
             double fl = 0;
-            for (int f = 0; f < nf1; f++) { waiting += h_nslots[f]; fl += 2.0 * p->h_folds[f].ntr * (double)p->kc * h_nslots[f]; }
-            if (timing) fprintf(stderr, "[pareben] stream round %d: %lld fits waiting\n", rounds, waiting);
+            long long waiting_a = 0;
+            for (int vf = 0; vf < nvf; vf++) { waiting += h_nslots[vf]; if (vf % STREAM_CLASSES == 0) waiting_a += h_nslots[vf]; fl += 2.0 * p->h_folds[vf / STREAM_CLASSES].ntr * (double)p->kc * h_nslots[vf]; }
+            if (timing) fprintf(stderr, "[pareben] stream round %d: %lld fits waiting (%lld with more than 7 active bases), last scan %.1f ms\n", rounds, waiting, waiting_a, last_scan_ms);
             if (waiting == 0) break;
             scan_flops += fl;
             CU(cudaEventRecord(es0, p->stream));
             scan();
             CU(cudaEventRecord(es1, p->stream));
             scans++;
-            CU(cudaMemsetAsync(d_nslots, 0, sizeof(int) * nf1, p->stream));
+            CU(cudaMemsetAsync(d_nslots, 0, sizeof(int) * nvf, p->stream));
             advance();
             rounds++;
         }

@@ -153,26 +153,52 @@ stream_advance_kernel(Problem P, Variant v, StreamFit *fits, int n_fits, StreamS
             for (int i = 1 + threadIdx.x; i < s.M; i += T) s.gamma[i] = 1.0 - s.sigma[i * s.M + i] * s.alpha[i];
             __syncthreads();
             s.beta_s = s.beta;
+            s.stats_valid = 0;                                                        // CacheBP + FullStat: everything is recomputed
             s.i_iter = 0; s.selected = ACT_NONE; s.n_update = 0; s.jj = -1;
             s.it_max = s.iter == 1 ? 10 : 100;
         }
         // ---------------- inner solver, one pass per scan ----------------
         for (;;) {
-            if (!resume) {
-                // request: publish e' and the screen, hand the fit to the scan kernel
+            // An iteration that applied no action and did not re-base the statistics leaves the reference's S/Q arrays
+            // untouched (even when FinalUpdate has meanwhile replaced SIGMA and Mu, :716-727): its next fEBDeltaML sees
+            // exactly what the last one saw.  Only a change asks for a new scan.
+            const bool reuse = !resume && s.stats_valid;
+            if (!resume && !reuse) {
+                // request: publish e' and the screens, hand the fit to the scan kernel
                 (void)stream_residual(s, N, LD, s.M, s.d, s.e, sc);
-                if (threadIdx.x == 0) s_slot = atomicAdd(sh.n_slots + s.fold, 1);
+                // right-hand-side class (stream.cuh): small active sets bring their columns along
+                const int Mq = s.M;
+                const int cls = (Mq == 1 && s.used[0] == 1) ? 1 : (!sh.wide ? 0 : (Mq <= 3 ? 2 : (Mq <= 7 ? 3 : 0)));
+                const int vf = STREAM_CLASSES * s.fold + cls;
+                if (threadIdx.x == 0) s_slot = atomicAdd(sh.n_slots + vf, 1);
                 __syncthreads();
-                const int slot = s_slot;
-                const StreamFold SF = sh.folds[s.fold];
-                double *E = SF.E + (size_t)(slot / SN) * e_tile_doubles(F.ldt) + (size_t)(slot % SN) * SLD;
-                for (int h = threadIdx.x; h < F.ldt; h += T) E[(size_t)(h / SK) * STAGE_D + (h % SK)] = h < N ? s.e[h] : 0.0;
+                const int idx = s_slot, per = class_fits_per_tile(cls);
+                const int slot = (idx / per) * SN + (cls == 1 ? 1 + idx % per : (idx % per) * class_width(cls));
+                const StreamFold SF = sh.folds[vf];
+                double *Et = SF.E + (size_t)(slot / SN) * e_tile_doubles(F.ldt);
+                double *E = Et + (size_t)(slot % SN) * SLD;
+                for (int h = threadIdx.x; h < F.ldt; h += T) {
+                    const size_t o = (size_t)(h / SK) * STAGE_D + (h % SK);
+                    E[o] = h < N ? s.e[h] : 0.0;
+                    if (cls == 1) Et[o] = h < N ? s.phi[h] : 0.0;          // every fit of the tile writes the same bytes
+                    if (cls >= 2)
+                        for (int j = 0; j < Mq; j++) E[(size_t)(1 + j) * SLD + o] = h < N ? s.phi[(size_t)j * LD + h] : 0.0;
+                }
                 if (threadIdx.x == 0) {
                     double thr_q2 = (2 * l1 + l2) * (1 - 1e-6) - 1e-10 * s.beta_s;       // Q^2 must exceed S + 2 l1 + l2 > this
                     if (!(thr_q2 > 0)) thr_q2 = 0;
-                    SF.thr[slot] = thr_q2 / (s.beta_s * s.beta_s);                      // Q = beta_s z / ||x||
+                    double inv = 1 / s.beta_s;
+                    for (int j = 0; j < s.M; j++) inv += 1 / s.alpha[j];
+                    double s_lb = 1 / inv - 1e-4 * s.beta_s;                             // slack: SIGMA follows beta to 1e-6 only
+                    if (!(s_lb > 0)) s_lb = 0;
+                    ScanSlot *sp = SF.par + slot;
+                    sp->bs = s.beta_s; sp->sig = s.sigma[0]; sp->l1 = l1; sp->l2 = l2; sp->s_lb = s_lb;
+                    for (int k = 0; k < 8; k++) sp->T[k] = 0;
+                    // (main effects keep screen 1 only: anyToAdd needs every a < 0)
+                    slot_thresholds(sp, v.ml_delta * (1 - 1e-9), thr_q2, EPIS);
+                    s.s_lb = s_lb;
                     SF.slot_fit[slot] = blockIdx.x;
-                    s.slot = slot; s.l1 = l1; s.l2 = l2; s.ml_delta = v.ml_delta; s.n_add = v.n_add;
+                    s.slot = slot; s.cls = cls; s.l1 = l1; s.l2 = l2; s.ml_delta = v.ml_delta; s.n_add = v.n_add;
                     s.runmax = 0ull; s.n_list = 0; s.any_add = 0;
                     s.phase = SP_WAIT;
                     s.flops += 2.0 * N * (double)P.Kc;
@@ -184,6 +210,7 @@ stream_advance_kernel(Problem P, Variant v, StreamFit *fits, int n_fits, StreamS
             s.i_iter++;
             const int M0 = s.M;
             // ---- statistics of the in-model candidates: g_j = column j of PHI'PHI ----
+            if (!reuse) {
             (void)stream_residual(s, N, LD, M0, s.d, s.e, sc);
             phi_t_vec(s.phi, N, LD, M0, s.e, s.q_in);                    // phi_j' e'
             for (int j = wid_; j < M0; j += nw_) {
@@ -196,6 +223,8 @@ stream_advance_kernel(Problem P, Variant v, StreamFit *fits, int n_fits, StreamS
                 quad = warp_sum(quad);
                 if (lane_ == 0) s.s_in[j] = s.beta_s - s.beta_s * quad * s.beta_s;
             }
+            }
+            s.stats_valid = 1;
             __syncthreads();
             // ---- fEBDeltaML (MainEff.c:1372-1582): in-model here, out-of-model from the scan's list ----
             int prio_add = 0, prio_del = 0;
@@ -461,6 +490,7 @@ stream_advance_kernel(Problem P, Variant v, StreamFit *fits, int n_fits, StreamS
                     }
                     __syncthreads();
                     if (updated) {                                                         // :657-681
+                        s.stats_valid = 0;
                         double *tmpp = s.sigma; s.sigma = s.sigma_new; s.sigma_new = tmpp;
                         const int Mn = s.M;
                         for (int i = threadIdx.x; i < Mn; i += T) s.gamma[i] = 1 - s.alpha[i] * s.sigma[i * Mn + i];
@@ -490,10 +520,11 @@ stream_advance_kernel(Problem P, Variant v, StreamFit *fits, int n_fits, StreamS
                     if (!spd_inverse_sweep(s.sigma, M, s.colk, sc, sc.sweep)) s.status |= ST_NOT_PD;
                     stream_posterior_mean(s, N, LD, M, s.beta);
                     // the FullStat that follows (unless terminating) re-bases the statistic arrays on the new beta; the
-                    // terminating case leaves the reference with stale arrays that only a forced delete can still read
-                    s.beta_s = s.beta;
-                    for (int h = threadIdx.x; h < N; h += T) s.d[h] = 0;
+                    // terminating case leaves the reference's arrays as they were
                     if (s.selected != ACT_TERM) {
+                        s.beta_s = s.beta;
+                        s.stats_valid = 0;
+                        for (int h = threadIdx.x; h < N; h += T) s.d[h] = 0;
                         for (int i = 1 + threadIdx.x; i < M; i += T) s.gamma[i] = 1.0 - s.sigma[i * M + i] * s.alpha[i];
                     }
                     __syncthreads();

@@ -104,10 +104,10 @@ def test_stream_real_valued_design(pb):
 
 
 def test_stream_many_fits_many_tiles(pb):
-    """More waiting fits than one 64-wide right-hand-side tile per fold, on a 400-locus design made with the config-5
-    recipe (80,200 candidates): the streamed table must equal the cached kernel's to rounding and be reproducible."""
+    """More waiting fits than one 64-wide right-hand-side tile per fold, on a 300-locus design made with the config-5
+    recipe (45,150 candidates): the streamed table must equal the cached kernel's to rounding and be reproducible."""
     rng = np.random.default_rng(20260101)
-    n, k = 240, 400
+    n, k = 600, 300
     X = _genotypes(rng, n, k, block=50, copy=0.9)
     beta = np.zeros(k); beta[rng.choice(k, 6, replace=False)] = rng.normal(0, 2.0, 6)
     pairs = rng.choice(k, (4, 2), replace=False)
