@@ -17,7 +17,10 @@ hold-out log-likelihood.
           shards are merged by one NCCL all-reduce of the three small tables (inside the e2e region;
           the resident `value` has no collective in it because the data path has none).
   extras  the same measurement on the bundled Gaussian data (1000 x 481, 10 folds, 4,000 fits --
-          four of the five BASELINE configs are Gaussian), sharded the same way.
+          four of the five BASELINE configs are Gaussian), sharded the same way; and BASELINE config 5's shape
+          (synthetic n = 1,000, Epis = "yes", 10 folds, the full 4,000-fit grid) through the streaming kernels:
+          k = 20,000 loci (200,010,000 candidates) when 8 GPUs share the grid, a k = 5,000 slice (12.5 M candidates)
+          on fewer, with the score-contraction kernel's own time, flops and fraction of the FP64 tensor peak.
   --impl reference   times the reference's own C (oracle/_ref, compiled unmodified from
           /root/reference/EBEN_orig/src) -- or the oracle's C restatement when that library is
           absent -- on all host cores: the whole 2,000-fit grid when --steps <= 2, else a
@@ -314,6 +317,39 @@ def run_gpu(args):
             "steps": g_steps, "algorithmic_tflops": g_ach, "roofline_frac": g_ach / (peak * world),
             "status_nonzero": int((rg["status"] != 0).sum()), "max_active_set": int(rg["nsel"].max())}
 
+        if not args.no_stream:
+            from pareben_b200.synth import config5
+            ks = args.stream_k if args.stream_k > 0 else (20000 if world >= 8 else 5000)
+            d5 = config5(1000, ks)
+            X5 = d5["X"].astype(np.float64); y5 = d5["y"]
+            folds5 = pb.AssignToFolds(X5, 10)
+            t_lm = time.perf_counter()
+            grid5 = pb.BuildGrid(X5, y5, 10, "yes", device=local)
+            t_lm = time.perf_counter() - t_lm
+            mine5 = pb.shard_plan(grid5["lambda"], 10, rank, world)
+            pb.set_mode(pb.MODE_STREAMING)
+            try:
+                with pb.Problem(X5, y5, folds5, 10, True, "gaussian", device=local) as p5:
+                    barrier()
+                    t5 = time.perf_counter()
+                    e5, st5, ns5, it5 = p5.run_fits((mine5 % 10 + 1).astype(np.int32), grid5["alpha"][mine5 // 10], grid5["lambda"][mine5 // 10])
+                    _fl5, ms5, launches5 = p5.counters()
+                    scan_ms, scan_fl, scans, rounds = p5.stream_counters()
+                    barrier()
+                    wall5 = max_over_ranks(time.perf_counter() - t5)
+            finally:
+                pb.set_mode(pb.MODE_AUTO)
+            job_ms = max_over_ranks(ms5)
+            tot_scan_fl = sum_over_ranks(scan_fl); max_scan_ms = max_over_ranks(scan_ms)
+            extras["config5_streaming"] = {
+                "workload": f"synthetic n=1000 x k={ks} Gaussian, Epis=yes ({ks * (ks + 1) // 2} candidates), 10 folds, 20x20 grid = 4000 fits, one grid split over the ranks",
+                "fits_per_step": 4000, "ms_per_step": job_ms, "fits_per_s": 4000 / (job_ms * 1e-3), "wall_s": wall5, "steps": 1,
+                "lambda_max_s": t_lm, "rounds": rounds, "kernel_launches_rank0": launches5,
+                "scan_kernel": {"name": "stream_scan_kernel<epis>", "launches_rank0": scans, "ms_total_max_over_ranks": max_scan_ms,
+                                "algorithmic_tflop": tot_scan_fl / 1e12, "achieved_tflops": tot_scan_fl / (max_scan_ms * 1e-3) / 1e12,
+                                "roofline_frac": tot_scan_fl / (max_scan_ms * 1e-3) / 1e12 / (peak_dmma * world)},
+                "status_nonzero": int(sum_over_ranks(float((st5 != 0).sum()))), "max_active_set": int(max_over_ranks(float(ns5.max())))}
+
     if rank == 0:
         achieved = res["flops"] / (res["ms_per_step"] * 1e-3) / 1e12
         cpu = None
@@ -366,6 +402,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the Gaussian extras")
+    ap.add_argument("--no-stream", action="store_true", help="skip the config-5 streaming extra")
+    ap.add_argument("--stream-k", type=int, default=0, help="loci of the config-5 streaming extra (0: 20000 on 8 GPUs, else 5000)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,6 +94,11 @@ int pareben_cv_grid(const double *basis, int n, int k, const double *target, con
                     int prior, int n_devices, int device, int shard, int n_shards, double *fold_err,
                     int *status, int *n_selected);
 
+/* pareben_cv_grid on a problem that is already resident (created with folds): BuildGrid's pareben_lambda_max, the
+ * grid and a LocalSearch refinement then share ONE upload and one set of per-fold layouts.  Same outputs, same shard rule. */
+int pareben_problem_cv_grid(pareben_problem *p, const double *alpha, const double *lambda, int n_grid, int shard,
+                            int n_shards, double *fold_err, int *status, int *n_selected);
+
 /* The shard assignment pareben_cv_grid uses, exposed for the host layer and tests (host-only
  * logic, needs no device): writes the ascending fit numbers of `shard` into fit_index
  * (capacity n_grid*n_folds) and their count into n_mine. */
@@ -108,6 +113,22 @@ int pareben_shard_plan(const double *lambda, int n_grid, int n_folds, int shard,
  *   MainEff.c:227) or log-likelihood (binomial, NEmainEff.c:805). */
 int pareben_fit(pareben_problem *p, double alpha, double lambda, double *beta_table, double *wald,
                 double *intercept, double *extra, int *status);
+
+/* EBEN's own four `.C` entry points, same names, argument lists and output layouts, as wrappers over
+ * pareben_problem_create + pareben_fit: an R session that loads this library in place of EBEN's (useDynLib / PACKAGE
+ * swapped) runs EBelasticNet.Gaussian / EBelasticNet.Binomial unchanged.  Replaces
+ *   EBEN_orig/src/elasticNetLinearNeMainEff.c:55-57     EBEN_orig/src/elasticNetLinearNeFull2.c:57-58
+ *   EBEN_orig/src/ElasticNetBinaryNEmainEff.c:236-238   EBEN_orig/src/ElasticNetBinaryNeFull.c:52-55
+ * (call sites EBEN_orig/R/EBelasticNet.Gaussian.R:16-28,39-51, EBelasticNet.Binomial.R:12-25,33-46).  Device:
+ * environment variable PAREBEN_DEVICE (default 0).  void like the originals; failures are reported on stderr. */
+void elasticNetLinearNeMainEff(double *BASIS, double *y, double *a_lambda, double *b_Alpha, double *Beta, double *wald,
+                               double *intercept, int *n, int *kdim, int *verb, double *residual);
+void elasticNetLinearNeEpisEff(double *BASIS, double *y, double *a_lambda, double *b_Alpha, double *Beta, double *wald,
+                               double *intercept, int *n, int *kdim, int *verb, double *residual);
+void ElasticNetBinaryNEmainEff(double *BASIS, double *Targets, double *a_Lambda, double *b_Alpha, double *logLIKELIHOOD,
+                               double *Beta, double *wald, double *intercept, int *n, int *kdim, int *VB, int *bMax);
+void ElasticNetBinaryNEfull(double *BASIS, double *Targets, double *a_Lambda, double *b_Alpha, double *logLIKELIHOOD,
+                            double *Beta, double *wald, double *intercept, int *n, int *kdim, int *VB, int *bMax);
 
 /* lambda_max of R/BuildGrid.R:5-32 (before the x10), computed on the device for the problem's
  * full data; epis taken from the problem. */

@@ -2,14 +2,14 @@
 # (R/CrossValidate.R:66-70 and :88-92) become one .Call.  Signature, return list and column names
 # are unchanged.  Folds: TestModel ignores the caller's foldId and recomputes them with
 # set.seed(1) inside every task (R/TestModel.R:9), so the same is done here, once.
-CrossValidate <- function(BASIS, Target, nFolds, foldId = 0, Epis = "no", prior = "gaussian", search = "global"){
+CrossValidate <- function(BASIS, Target, nFolds, foldId = 0, Epis = "no", prior = "gaussian", search = "global", nDevices = 0L){
   if(search == "global"){
     ParameterGrid <- BuildGrid(BASIS, Target, nFolds, Epis)
     folds <- AssignToFolds(BASIS, nFolds)
     storage.mode(BASIS) <- "double"
     res <- .Call("pareben_cv_grid_call", BASIS, as.double(Target), as.integer(folds), as.integer(nFolds),
                  as.double(ParameterGrid$alpha), as.double(ParameterGrid$lambda),
-                 as.integer(Epis == "yes"), as.integer(prior != "gaussian"), 0L, PACKAGE = "parEBEN")
+                 as.integer(Epis == "yes"), as.integer(prior != "gaussian"), as.integer(nDevices), 0L, PACKAGE = "parEBEN")   # nDevices = 0: every GPU of the box
     if(any(res$status != 0)) warning(sum(res$status != 0), " fits finished with a non-zero status")
     detail <- data.frame(foldId = rep(1:nFolds, nrow(ParameterGrid)),
                          alpha  = rep(ParameterGrid$alpha,  each = nFolds),
@@ -28,6 +28,6 @@ CrossValidate <- function(BASIS, Target, nFolds, foldId = 0, Epis = "no", prior 
     list(Results.Detail = detail, Results.Summary = Error,
          lambda.optimal = Error[index,]$lambda, alpha.optimal = Error[index,]$alpha)
   }else{
-    LocalSearch(BASIS, Target, nFolds, Epis, foldId, prior)
+    LocalSearch(BASIS, Target, nFolds, Epis, foldId, prior, nDevices)   # integration/r/LocalSearch_gpu.R
   }
 }

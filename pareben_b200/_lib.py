@@ -31,6 +31,11 @@ SIGNATURES = {
     "pareben_cv_grid": (ctypes.c_int, [_dp, ctypes.c_int, ctypes.c_int, _dp, _ip, ctypes.c_int, _dp, _dp, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _ip,
                                        _ip]),
+    "pareben_problem_cv_grid": (ctypes.c_int, [_vp, _dp, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _ip, _ip]),
+    "elasticNetLinearNeMainEff": (None, [_dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _dp]),
+    "elasticNetLinearNeEpisEff": (None, [_dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _dp]),
+    "ElasticNetBinaryNEmainEff": (None, [_dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _ip]),
+    "ElasticNetBinaryNEfull": (None, [_dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _ip]),
     "pareben_shard_plan": (ctypes.c_int, [_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _ip, _ip]),
     "pareben_fit": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, _dp, _dp, _dp, _dp, _ip]),
     "pareben_lambda_max": (ctypes.c_int, [_vp, _dp]),
@@ -157,11 +162,8 @@ class Problem:
         if alpha.size != lam.size or self.n_folds < 1:
             raise ValueError("alpha and lambda must have equal length and the problem must have folds")
         nf, total = self.n_folds, alpha.size * self.n_folds
-        mine = shard_plan(lam, nf, shard, n_shards)
         err = np.zeros(total); st = np.zeros(total, np.int32); ns = np.zeros(total, np.int32)
-        if mine.size:
-            e, s_, n_, _ = self.run_fits(mine % nf + 1, alpha[mine // nf], lam[mine // nf])
-            err[mine] = e; st[mine] = s_; ns[mine] = n_
+        _check(load().pareben_problem_cv_grid(self._h, _d(alpha), _d(lam), alpha.size, int(shard), int(n_shards), _d(err), _i(st), _i(ns)))
         return err.reshape(alpha.size, nf), st.reshape(alpha.size, nf), ns.reshape(alpha.size, nf)
 
     def fit(self, alpha: float, lam: float):

@@ -506,7 +506,7 @@ __device__ void binom_fit(const Problem &P, const FoldData &F, const Variant &v,
         }
         ll = block_sum(ll, sc) / F.nte;
     }
-    if (!isfinite(ll)) b.status |= ST_NONFINITE;
+    if (F.nte > 0 && !isfinite(ll)) b.status |= ST_NONFINITE;      // (no held-out rows in an all-rows fit: nothing to score)
     if (threadIdx.x == 0) {
         const int o = task.out_index;
         if (out.fold_err) out.fold_err[o] = ll;

@@ -1302,6 +1302,7 @@ __device__ inline Decision delta_ml(Slab &s, int M, int N, int Kc, double lambda
     int f_add = 0, f_del = 0;
     for (int c = threadIdx.x; c < Kc; c += blockDim.x) {
         const int i = s.amap[c];
+        if (i == -2) { s.dml[c] = 0; s.action[c] = ACT_NONE; continue; }      // in neither Used nor Unused (see the delete action)
         const double so = s.S_out[c], qo = s.Q_out[c];
         double d_ml = 0; int act = ACT_NONE;
         const double a = so - qo * qo + 2 * l1 + l2;
@@ -1604,8 +1605,15 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             s.mu[jj] = s.mu[lastj];
                             const int gr = s.grow[jj]; s.grow[jj] = s.grow[lastj]; s.grow[lastj] = gr;
                             const int moved = s.used[lastj];
+                            // The basis that leaves is the one in slot jj.  That is candidate nu, except in the forced
+                            // removal of an initial basis that a regular delete has already taken out (:437-446): the
+                            // reference's search of Used then fails, jj keeps its previous value and ANOTHER basis is
+                            // dropped -- while it is candidate nu that is appended to Unused (:621-625).  The dropped one
+                            // is then in neither list: no scan sees it until Unused is rebuilt at the next outer
+                            // iteration (:1092-1107).  amap = -2 reproduces that.
+                            const int dropped = s.used[jj] - 1;
                             s.used[jj] = moved;
-                            s.amap[nu] = -1;
+                            s.amap[dropped] = dropped == nu ? -1 : -2;
                             if (jj != lastj) s.amap[moved - 1] = jj;
                             s.unused[g.n_unused] = nu + 1; s.upos[nu] = g.n_unused;
                             g.flops += 2.0 * Kc * (double)M;

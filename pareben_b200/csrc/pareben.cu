@@ -958,6 +958,90 @@ extern "C" int pareben_fit(pareben_problem *p, double alpha, double lambda, doub
     return PAREBEN_OK;
 }
 
+// The grid call on a problem that is already resident (one upload serves BuildGrid's lambda_max, the grid and any
+// LocalSearch refinement): same table layout and shard assignment as pareben_cv_grid.
+extern "C" int pareben_problem_cv_grid(pareben_problem *p, const double *alpha, const double *lambda, int n_grid, int shard,
+                                       int n_shards, double *fold_err, int *status, int *n_selected)
+{
+    if (!p || !alpha || !lambda || !fold_err || n_grid < 1) return fail(PAREBEN_EINVAL, "pareben_problem_cv_grid: bad argument");
+    if (p->n_folds < 1) return fail(PAREBEN_EINVAL, "pareben_problem_cv_grid needs a problem created with folds");
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(PAREBEN_EINVAL, "pareben_problem_cv_grid: bad shard");
+    const int nf = p->n_folds, total = n_grid * nf;
+    std::vector<int> mine(total);
+    int m = 0;
+    int rc = pareben_shard_plan(lambda, n_grid, nf, shard, n_shards, mine.data(), &m);
+    if (rc != PAREBEN_OK || m == 0) return rc;
+    std::vector<int> fold(m), st(m), ns(m);
+    std::vector<double> a(m), l(m), err(m);
+    for (int i = 0; i < m; i++) { fold[i] = mine[i] % nf + 1; a[i] = alpha[mine[i] / nf]; l[i] = lambda[mine[i] / nf]; }
+    rc = pareben_run_fits(p, m, fold.data(), a.data(), l.data(), err.data(), st.data(), ns.data(), nullptr);
+    if (rc != PAREBEN_OK) return rc;
+    for (int i = 0; i < m; i++) {
+        fold_err[mine[i]] = err[i];
+        if (status) status[mine[i]] = st[i];
+        if (n_selected) n_selected[mine[i]] = ns[i];
+    }
+    return PAREBEN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The four `.C` entry points of EBEN, same names and argument lists (MainEff.c:55-57, NeFull2.c:57-58,
+// NEmainEff.c:236-238, NeFull.c:52-55), as thin wrappers over pareben_fit: with useDynLib pointed at this library the
+// R wrappers EBelasticNet.Gaussian / EBelasticNet.Binomial (EBEN_orig/R) run unchanged on the GPU.  Like the originals
+// they return nothing; a failure is reported on stderr (where the shimmed Rprintf of the reference writes) and leaves
+// the outputs zeroed.
+namespace {
+void dot_c_fit(const char *name, double *BASIS, double *y, double lambda, double alpha, double *Beta, double *wald, double *intercept,
+               int n, int k, int epis, int prior, double *extra, int beta_rows, int beta_cols)
+{
+    for (size_t i = 0, e = (size_t)beta_rows * beta_cols; i < e; i++) Beta[i] = 0;
+    if (wald) wald[0] = 0;
+    if (intercept) { intercept[0] = 0; if (prior == PAREBEN_BINOMIAL) intercept[1] = 0; }
+    if (extra) extra[0] = 0;
+    int dev = 0;
+    if (const char *e = getenv("PAREBEN_DEVICE")) dev = atoi(e);
+    pareben_problem *p = nullptr;
+    int rc = pareben_problem_create(&p, dev, BASIS, n, k, y, nullptr, 0, epis, prior);
+    int st = 0;
+    if (rc == PAREBEN_OK) rc = pareben_fit(p, alpha, lambda, Beta, wald, intercept, extra, &st);
+    if (p) pareben_problem_destroy(p);
+    if (rc != PAREBEN_OK) fprintf(stderr, "%s (libpareben): error %d: %s\n", name, rc, pareben_last_error());
+    else if (st != 0) fprintf(stderr, "%s (libpareben): fit finished with status %d\n", name, st);
+}
+}  // namespace
+
+extern "C" void elasticNetLinearNeMainEff(double *BASIS, double *y, double *a_lambda, double *b_Alpha, double *Beta, double *wald,
+                                          double *intercept, int *n, int *kdim, int *verb, double *residual)
+{
+    (void)verb;
+    dot_c_fit("elasticNetLinearNeMainEff", BASIS, y, *a_lambda, *b_Alpha, Beta, wald, intercept, *n, *kdim, 0, PAREBEN_GAUSSIAN, residual, *kdim, 4);
+}
+
+extern "C" void elasticNetLinearNeEpisEff(double *BASIS, double *y, double *a_lambda, double *b_Alpha, double *Beta, double *wald,
+                                          double *intercept, int *n, int *kdim, int *verb, double *residual)
+{
+    (void)verb;
+    const int k = *kdim;
+    dot_c_fit("elasticNetLinearNeEpisEff", BASIS, y, *a_lambda, *b_Alpha, Beta, wald, intercept, *n, k, 1, PAREBEN_GAUSSIAN, residual,
+              (int)((long long)k * (k + 1) / 2), 5);
+}
+
+extern "C" void ElasticNetBinaryNEmainEff(double *BASIS, double *Targets, double *a_Lambda, double *b_Alpha, double *logLIKELIHOOD,
+                                          double *Beta, double *wald, double *intercept, int *n, int *kdim, int *VB, int *bMax)
+{
+    (void)VB; (void)bMax;                     // bMax = k for main effects (EBelasticNet.Binomial.R:30): the table is k x 4
+    dot_c_fit("ElasticNetBinaryNEmainEff", BASIS, Targets, *a_Lambda, *b_Alpha, Beta, wald, intercept, *n, *kdim, 0, PAREBEN_BINOMIAL,
+              logLIKELIHOOD, *kdim, 4);
+}
+
+extern "C" void ElasticNetBinaryNEfull(double *BASIS, double *Targets, double *a_Lambda, double *b_Alpha, double *logLIKELIHOOD,
+                                       double *Beta, double *wald, double *intercept, int *n, int *kdim, int *VB, int *bMax)
+{
+    (void)VB; (void)bMax;                     // bMax = 2k for Epis (EBelasticNet.Binomial.R:8): the table is 2k x 4, compact
+    dot_c_fit("ElasticNetBinaryNEfull", BASIS, Targets, *a_Lambda, *b_Alpha, Beta, wald, intercept, *n, *kdim, 1, PAREBEN_BINOMIAL,
+              logLIKELIHOOD, 2 * *kdim, 4);
+}
+
 extern "C" int pareben_lambda_max(pareben_problem *p, double *lambda_max)
 {
     if (!p || !lambda_max) return fail(PAREBEN_EINVAL, "pareben_lambda_max: bad argument");

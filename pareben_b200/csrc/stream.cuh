@@ -61,6 +61,7 @@ struct StreamFit {
     // control state of the solver between two rounds (the loop-carried scalars of gauss_fit())
     int phase;
     int iter, i_iter, selected, ini_removed, n_update, jj, it_max, initial, M, status;
+    int n_hidden, hidden[4];                // candidates in neither Used nor Unused until the next outer iteration (see the delete action)
     int stats_valid;                        // nothing has touched the statistic arrays since the last fEBDeltaML: the next one sees the same S, Q
     double beta, beta_s, b, vk, vk0, err, residvar, var_y, flops;
     // scan interface (meaningful while phase == SP_WAIT)

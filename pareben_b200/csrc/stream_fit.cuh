@@ -154,6 +154,7 @@ stream_advance_kernel(Problem P, Variant v, StreamFit *fits, int n_fits, StreamS
             __syncthreads();
             s.beta_s = s.beta;
             s.stats_valid = 0;                                                        // CacheBP + FullStat: everything is recomputed
+            s.n_hidden = 0;                                                           // Unused is rebuilt from Used (:1092-1107)
             s.i_iter = 0; s.selected = ACT_NONE; s.n_update = 0; s.jj = -1;
             s.it_max = s.iter == 1 ? 10 : 100;
         }
@@ -480,6 +481,11 @@ stream_advance_kernel(Problem P, Variant v, StreamFit *fits, int n_fits, StreamS
                             }
                         }
                         __syncthreads();
+                        // the basis that leaves is the one in slot jj: not candidate nu when the forced removal's search of Used
+                        // failed (gauss_fit.cuh, delete action) -- it is then in neither list until the next outer iteration
+                        const int dropped = s.used[jj] - 1;
+                        __syncthreads();
+                        if (dropped != nu && s.n_hidden < 4) { s.hidden[s.n_hidden] = dropped; s.n_hidden++; }
                         if (threadIdx.x == 0) {
                             s.alpha[jj] = al_last; s.ascale[jj] = sc_last;
                             s.mu[jj] = s.mu[lastj];

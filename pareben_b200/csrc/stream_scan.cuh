@@ -83,6 +83,7 @@ template <bool GAUSS_MAIN>
 __device__ inline double scan_decide(StreamFit *fit, int c, double so, double qo, int list_cap)
 {
     const double l1 = fit->l1, l2 = fit->l2;
+    for (int h = 0; h < fit->n_hidden; h++) if (fit->hidden[h] == c) return 0.0;       // in neither Used nor Unused
     const double a = so - qo * qo + 2 * l1 + l2;
     const double b = (so + l2) * (so + 4 * l1 + l2);
     const double gm = 2 * l1 * (so + l2) * (so + l2);

@@ -13,13 +13,15 @@ from conftest import ROOT
 def _declared():
     text = open(os.path.join(ROOT, "include", "pareben.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(pareben_[a-z0-9_]+)\s*\(", text)))
+    # pareben_* plus EBEN's own four `.C` entry points, which the library exports under their original names
+    return sorted(set(re.findall(r"\b(pareben_[a-z0-9_]+|elasticNetLinearNe(?:MainEff|EpisEff)|ElasticNetBinaryNE(?:mainEff|full))\s*\(", text)))
 
 
 def test_header_symbols_exported(built):
     import pareben_b200 as pb
     names = _declared()
     assert "pareben_cv_grid" in names and "pareben_fit" in names and len(names) >= 10
+    assert {"elasticNetLinearNeMainEff", "elasticNetLinearNeEpisEff", "ElasticNetBinaryNEmainEff", "ElasticNetBinaryNEfull"} <= set(names)
     lib = ctypes.CDLL(pb._lib.LIB_PATH)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/pareben.h but not exported"

@@ -1,0 +1,140 @@
+"""GPU suite (-m gpu), part 4: the boundary an EBEN / parEBEN maintainer binds.
+
+  * EBEN's four `.C` entry points, exported by libpareben.so under their original names and argument lists
+    (EBEN_orig/src/elasticNetLinearNeMainEff.c:55-57, elasticNetLinearNeFull2.c:57-58,
+    ElasticNetBinaryNEmainEff.c:236-238, ElasticNetBinaryNeFull.c:52-55), called through ctypes exactly as R's `.C`
+    would (every argument a pointer) and compared with the oracle library called the same way;
+  * the final-model tables of the Epis variants: Gaussian k(k+1)/2 x 5 indexed by candidate (loc1, loc2, beta, var,
+    used id; EBelasticNet.Gaussian.R:56-98) and binomial 2k x 4 compact in `Used` order with decoded loci
+    (ElasticNetBinaryNeFull.c:168-208);
+  * the resident-problem grid call that lets BuildGrid and CrossValidate share one upload.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import rlayer as R
+
+pytestmark = pytest.mark.gpu
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+@pytest.fixture(scope="module")
+def pb(built):
+    import pareben_b200 as pb
+    if pb.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu suite must run on the B200 box")
+    return pb
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _dot_c_gaussian(fn, X, y, lam, alpha, epis):
+    n, k = X.shape
+    rows, cols = ((k + 1) * k // 2, 5) if epis else (k, 4)
+    Xf = np.asfortranarray(X, dtype=np.float64); yc = np.ascontiguousarray(y, dtype=np.float64)
+    beta = np.full(rows * cols, 7.0); wald = np.zeros(1); icpt = np.zeros(1); resid = np.zeros(1)
+    fn(_p(Xf), _p(yc), _p(np.array([lam])), _p(np.array([alpha])), _p(beta), _p(wald), _p(icpt),
+       ctypes.byref(ctypes.c_int(n)), ctypes.byref(ctypes.c_int(k)), ctypes.byref(ctypes.c_int(0)), _p(resid))
+    return beta.reshape((rows, cols), order="F"), wald[0], icpt[0], resid[0]
+
+
+def _dot_c_binomial(fn, X, y, lam, alpha, epis):
+    n, k = X.shape
+    rows = 2 * k if epis else k
+    Xf = np.asfortranarray(X, dtype=np.float64); yc = np.ascontiguousarray(y, dtype=np.float64)
+    beta = np.zeros(rows * 4); wald = np.zeros(1); icpt = np.zeros(2); logl = np.zeros(1)
+    fn(_p(Xf), _p(yc), _p(np.array([lam])), _p(np.array([alpha])), _p(logl), _p(beta), _p(wald), _p(icpt),
+       ctypes.byref(ctypes.c_int(n)), ctypes.byref(ctypes.c_int(k)), ctypes.byref(ctypes.c_int(0)), ctypes.byref(ctypes.c_int(rows)))
+    return beta.reshape((rows, 4), order="F"), wald[0], icpt.copy(), logl[0]
+
+
+def _same_table(got, want, value_cols, rtol=1e-8):
+    assert got.shape == want.shape
+    assert np.array_equal(got[:, :2], want[:, :2])                       # loci columns
+    for c in value_cols:
+        assert np.array_equal(got[:, c] != 0, want[:, c] != 0)
+        assert np.allclose(got[:, c], want[:, c], rtol=rtol, atol=1e-14)
+
+
+def _data(seed, n, k):
+    rng = np.random.default_rng(seed)
+    X = rng.choice([-1.0, 0.0, 1.0], size=(n, k), p=[0.25, 0.5, 0.25])
+    y = 20 + 2.5 * X[:, 1] - 2.0 * X[:, k // 2] + 2.2 * X[:, 3] * X[:, k - 2] + rng.normal(0, 1.5, n)
+    eta = 1.3 * X[:, 1] - 1.1 * X[:, k // 2] + 1.4 * X[:, 3] * X[:, k - 2]
+    yb = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float)
+    return X, y, yb
+
+
+def test_dot_c_symbols_match_the_reference_argument_lists(pb):
+    lib = pb.load()
+    ref = R.fit_lib(R.available_kind())
+    X, y, yb = _data(3, 160, 24)
+    # (hyper-parameters chosen so that no active set comes near the reference's basisMax = 2k: it writes past its
+    #  buffers there, SURVEY fact 6 -- checked with the C restatement, which stops instead)
+    for epis, mine, theirs in ((False, lib.elasticNetLinearNeMainEff, ref.g_main), (True, lib.elasticNetLinearNeEpisEff, ref.g_epis)):
+        for lam, alpha in (((0.6, 1.0), (0.08, 0.4)) if not epis else ((1.5, 1.0), (0.6, 0.5))):
+            got = _dot_c_gaussian(mine, X, y, lam, alpha, epis)
+            want = _dot_c_gaussian(theirs, X, y, lam, alpha, epis)
+            _same_table(got[0], want[0], (2, 3) + ((4,) if epis else ()))
+            assert (got[0][:, 2] != 0).sum() >= 1
+            for a, b in zip(got[1:], want[1:]):
+                assert abs(a - b) <= 1e-8 * abs(b)
+    for epis, mine, theirs in ((False, lib.ElasticNetBinaryNEmainEff, ref.b_main), (True, lib.ElasticNetBinaryNEfull, ref.b_epis)):
+        for lam, alpha in (((0.3, 1.0), (0.06, 0.5)) if not epis else ((0.3, 1.0), (0.15, 0.5))):
+            got = _dot_c_binomial(mine, X, yb, lam, alpha, epis)
+            want = _dot_c_binomial(theirs, X, yb, lam, alpha, epis)
+            _same_table(got[0], want[0], (2, 3), rtol=1e-7)
+            assert abs(got[1] - want[1]) <= 1e-7 * abs(want[1])
+            assert np.allclose(got[2], want[2], rtol=1e-7)
+            assert abs(got[3] - want[3]) <= 1e-7 * abs(want[3])
+
+
+def test_epis_final_model_tables(pb):
+    """pareben_fit layouts for Epis: Gaussian Kc x 5 by candidate id, binomial 2k x 4 compact in Used order."""
+    ref = R.fit_lib(R.available_kind())
+    X, y, yb = _data(5, 200, 30)
+    k = X.shape[1]
+    fit = R.eb_elastic_net_gaussian(X, y, 0.3, 0.5, True, ref)              # 14 effects, 12 of them pairs (basisMax = 60)
+    with pb.Problem(X, y, None, 0, True, "gaussian") as p:
+        table, wald, icpt, resid, st = p.fit(0.5, 0.3)
+    assert st == 0 and table.shape == (k * (k + 1) // 2, 5)
+    _same_table(table, fit.raw_beta, (2, 3, 4))
+    used = table[:, 4][table[:, 4] != 0]
+    assert used.size >= 3 and np.array_equal(np.sort(used), np.flatnonzero(table[:, 4]) + 1)     # column 5 holds the candidate's own 1-based id
+    assert np.any(table[table[:, 4] != 0, 0] != table[table[:, 4] != 0, 1])                      # at least one pair effect
+    assert abs(icpt[0] - fit.intercept[0]) <= 1e-8 * abs(fit.intercept[0]) and abs(wald - fit.wald) <= 1e-8 * abs(fit.wald)
+    assert abs(resid - fit.resid_var) <= 1e-8 * fit.resid_var
+    w = pb.EBelasticNet_Gaussian(X, y, 0.3, 0.5, "yes")["weight"]
+    assert w.shape == fit.weight.shape and np.allclose(w[:, :5], fit.weight[:, :5], rtol=1e-8)
+
+    fitb = R.eb_elastic_net_binomial(X, yb, 0.15, 0.5, True, ref)           # 37 effects of bMax = 60
+    with pb.Problem(X, yb, None, 0, True, "binomial") as p:
+        tb, waldb, icptb, logl, stb = p.fit(0.5, 0.15)
+    assert stb == 0 and tb.shape == (2 * k, 4)
+    m = int((fitb.raw_beta[:, 2] != 0).sum())
+    assert m >= 2 and np.all(tb[m:] == 0)                                                        # compact: rows past the active set are zero
+    _same_table(tb, fitb.raw_beta, (2, 3), rtol=1e-7)
+    assert np.allclose(icptb, fitb.intercept, rtol=1e-7) and abs(logl - fitb.log_likelihood) <= 1e-7 * abs(fitb.log_likelihood)
+
+
+def test_resident_problem_serves_lambda_max_and_grid(pb):
+    """BuildGrid -> CrossValidate on ONE upload: pareben_lambda_max and pareben_problem_cv_grid on the same handle give
+    what the two separate host-buffer calls give, shards included."""
+    X, y, _ = _data(9, 120, 40)
+    folds = R.assign_to_folds(120, 4)
+    with pb.Problem(X, y, folds, 4, False, "gaussian") as p:
+        lm = p.lambda_max()
+        grid = pb.cross_validate._grid_from_lambda_max(lm)
+        rows = np.arange(0, 400, 9)
+        a, l = grid["alpha"][rows], grid["lambda"][rows]
+        whole = p.cv_grid(a, l)
+        parts = [p.cv_grid(a, l, s, 3) for s in range(3)]
+    assert abs(lm - pb.GetLambdaMax(X, y)) <= 1e-14 * lm
+    direct = pb.cv_grid(X, y, folds, 4, a, l)
+    for i in range(3):
+        assert np.array_equal(whole[i], direct[i])
+        assert np.array_equal(sum(pt[i] for pt in parts), whole[i])

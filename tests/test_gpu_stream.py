@@ -126,3 +126,47 @@ def test_stream_many_fits_many_tiles(pb):
     err_c, st_c, ns_c = pb.cv_grid(X, y, folds, 2, alpha, lam, epis=True)
     assert np.array_equal(ns_a, ns_c)
     assert np.max(np.abs(err_a - err_c) / np.abs(err_c)) < 1e-8
+
+
+def test_stream_k2000_slice_against_reference_fixture(pb):
+    """K = 2,000 loci of the config-5 recipe, Epis = "yes": 2,001,000 candidates, the golden values of
+    tests/golden/make_stream_golden.py (the reference's own C).  Rows of BuildGrid's own grid keep one basis (the
+    regime of config 5 at full size); lambda = 0.07 builds ~110 effects out of two million candidates."""
+    from conftest import golden
+    from pareben_b200.synth import config5
+    g = golden("stream_k2000.npz")
+    d = config5(int(g["n"]), int(g["k"]), int(g["seed"]))
+    X = d["X"].astype(np.float64); y = d["y"]
+    assert np.array_equal(y[:8], g["y_check"])                       # the generator reproduces the fixture's data
+    nf = int(g["n_folds"])
+    folds = g["fold_id"]
+    have = np.isfinite(g["fold_err"])
+    gi, fi = np.nonzero(have)
+    assert abs(pb.GetLambdaMax(X, y, "yes") - float(g["lambda_max"])) <= 1e-12 * float(g["lambda_max"])
+    pb.set_mode(pb.MODE_STREAMING)
+    try:
+        with pb.Problem(X, y, folds, nf, epis=True) as prob:
+            assert prob.streaming
+            err, st, ns, it = prob.run_fits(fi + 1, g["alpha"][gi], g["lam"][gi])
+    finally:
+        pb.set_mode(pb.MODE_AUTO)
+    assert np.all(st == 0)
+    want_e, want_m = g["fold_err"][gi, fi], g["n_selected"][gi, fi]
+    assert np.array_equal(ns, want_m), (ns, want_m)
+    assert ns.max() >= 100
+    rel = np.abs(err - want_e) / np.abs(want_e)
+    assert rel.max() < 1e-8, rel
+
+
+def test_stream_wide_classes_give_the_same_table(pb, monkeypatch):
+    """PAREBEN_STREAM_WIDE=1 routes fits with up to 7 active bases through the 4- and 8-column right-hand-side classes
+    (their S is exact in the scan's epilogue); the table must not depend on that choice beyond rounding."""
+    rng = np.random.default_rng(7)
+    n, k = 200, 60
+    X = _genotypes(rng, n, k, block=10)
+    y = 50 + 2.5 * X[:, 3] - 2.0 * X[:, 40] + 3.0 * X[:, 7] * X[:, 22] - 2.5 * X[:, 31] * X[:, 55] + rng.normal(0, 2.0, n)
+    lam = np.array([1.5, 0.4, 0.1, 0.03]); alpha = np.array([1.0, 0.5, 0.1, 0.7])
+    err_n, _ = _stream_vs_oracle(pb, X, y, 3, lam, alpha, True)
+    monkeypatch.setenv("PAREBEN_STREAM_WIDE", "1")
+    err_w, _ = _stream_vs_oracle(pb, X, y, 3, lam, alpha, True)
+    assert np.max(np.abs(err_w - err_n) / np.abs(err_n)) < 1e-9
