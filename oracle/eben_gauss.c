@@ -7,7 +7,7 @@
  *                                ActionAdd 1585-1723, ActionDel 1725-1822, FinalUpdate 1841-1921
  *   elasticNetLinearNeFull2.c    same skeleton with K(K+1)/2 candidates (entry 57-261) and the
  *                                constants that differ (SURVEY.md Appendix A "variant constant table").
- * Parity is pinned by tests/test_oracle_port.py against oracle/_ref/libeben_ref.so (the
+ * Parity is pinned by tests/test_oracle.py (test_port_*) against oracle/_ref/libeben_ref.so (the
  * reference C compiled unmodified here) and against tests/golden/ vectors generated from it;
  * summation order differs from OpenBLAS inside ddot/dgemv/dgemm/dpotrf, so agreement is to
  * rounding (rel <= 1e-9 on fold errors, identical supports), not bit-for-bit.
@@ -18,6 +18,17 @@
 #include <string.h>
 
 enum { ACT_REEST = 0, ACT_ADD = 1, ACT_DEL = -1, ACT_TERM = 10, ACT_NONE = -10 };
+
+/* Test switch (tests/test_oracle.py::test_streaming_identity, scripts/stream_equivalence.py): when set, the statistic
+ * arrays S_in / Q_in are NOT corrected incrementally by the actions but recomputed after every action from the
+ * active set alone,
+ *     S_c = beta_s - beta_s^2 g_c' SIGMA g_c,     Q_c = beta_s (x_c' t / s_c - g_c' mu) - (ghost term),
+ * beta_s = the noise precision of the last FullStat, ghost term = beta * G[j][c] * mu'_j summed over the bases j deleted
+ * since then (the remainder the reference's `int Mujj` truncation leaves behind, MainEff.c:1746).  This is the identity
+ * the streaming kernels (pareben_b200/csrc/stream.cuh) are built on; the switch exists to demonstrate it against the
+ * unmodified path on the CPU. */
+static int g_fresh_statistics = 0;
+void oracle_set_fresh_statistics(int on) { g_fresh_statistics = on; }
 
 typedef struct {
     int epis;              /* 0 main, 1 pairwise */
@@ -46,6 +57,8 @@ typedef struct {
     int *action, *block;
     double beta;
     int overflow;
+    double beta_stat;      /* fresh-statistics test switch: beta of the last FullStat */
+    double *qcorr;         /* Kc: ghost term of the deleted bases since the last FullStat */
 } State;
 
 static void column(const State *s, int c, double *out)
@@ -189,6 +202,8 @@ static void full_stat(State *s, const double *t, int first)
         s->H[0] = h * s->beta + s->alpha[0];
         s->sigma[0] = 1 / s->H[0];
     }
+    s->beta_stat = s->beta;
+    if (s->qcorr) memset(s->qcorr, 0, sizeof(double) * s->Kc);
     posterior_mean(s, t);
     for (int i = 1; i < M; i++) s->gamma[i] = 1 - s->sigma[i * M + i] * s->alpha[i];   /* gamma[0] skipped, :1283 */
     double *bp = malloc(sizeof(double) * M);
@@ -364,6 +379,7 @@ static void action_delete(State *s, int jj)
     const double *sj = s->sigma + jj * M;
     double sjj = sj[jj];
     for (int i = 0; i < M; i++) s->mu[i] = s->mu[i] - mujj * sj[i] / sjj;
+    if (s->qcorr) { const double left = s->mu[jj]; for (int c = 0; c < s->Kc; c++) s->qcorr[c] += s->beta * s->G[jj][c] * left; }
     s->mu[jj] = s->mu[last];
     double *tmp = malloc(sizeof(double) * M * M);
     for (int i = 0; i < M; i++)
@@ -385,8 +401,25 @@ static void action_delete(State *s, int jj)
     double *p = s->G[jj]; s->G[jj] = s->G[last]; s->G[last] = p;
 }
 
+static void fresh_statistics(State *s)
+{   /* the streaming identity: S_in, Q_in from (SIGMA_new, mu, the cache, beta_stat, ghost term) alone */
+    int M = s->M;
+    const double *sg = s->sigma_new, bs = s->beta_stat;
+    double *bp = malloc(sizeof(double) * M);
+    for (int c = 0; c < s->Kc; c++) {
+        for (int j = 0; j < M; j++) { double z = 0; for (int p = 0; p < M; p++) z += s->G[p][c] * sg[j * M + p]; bp[j] = z; }
+        double quad = 0, gm = 0;
+        for (int j = 0; j < M; j++) quad += bp[j] * s->G[j][c];
+        for (int p = 0; p < M; p++) gm += s->G[p][c] * s->mu[p];
+        s->S_in[c] = bs - bs * quad * bs;
+        s->Q_in[c] = bs * (s->xt[c] - gm) - s->qcorr[c];
+    }
+    free(bp);
+}
+
 static void after_action(State *s)
 {   /* MainEff.c:657-681 */
+    if (g_fresh_statistics) fresh_statistics(s);
     refresh_out(s);
     memcpy(s->sigma, s->sigma_new, sizeof(double) * s->M * s->M);
     for (int i = 0; i < s->M; i++) s->gamma[i] = 1 - s->alpha[i] * s->sigma[i * s->M + i];
@@ -528,6 +561,7 @@ static void fit(const Variant *v, const double *X, const double *y, double lambd
     s.S_out = calloc(Kc, sizeof(double)); s.Q_out = calloc(Kc, sizeof(double));
     s.dml = calloc(Kc, sizeof(double)); s.aroot = calloc(Kc, sizeof(double));
     s.action = calloc(Kc, sizeof(int)); s.block = calloc(Kc, sizeof(int));
+    s.qcorr = g_fresh_statistics ? calloc(Kc, sizeof(double)) : NULL;
     s.M = 1;
     double *t = malloc(sizeof(double) * N);
     double b = 0;
@@ -589,6 +623,7 @@ static void fit(const Variant *v, const double *X, const double *y, double lambd
     free(loc1); free(loc2); free(s.scale); free(s.used); free(s.unused); free(s.alpha); free(s.mu); free(s.gamma);
     free(s.sigma); free(s.sigma_new); free(s.H); free(s.phi); free(s.G); free(s.xt);
     free(s.S_in); free(s.Q_in); free(s.S_out); free(s.Q_out); free(s.dml); free(s.aroot); free(s.action); free(s.block);
+    free(s.qcorr);
 }
 
 static const Variant G_MAIN = { 0, 0.9, 1e-3, 1e-3, 1e2 };

@@ -150,3 +150,15 @@ def test_sl_prefilter_matches_the_r_script(pb, bundled):
             assert np.allclose(got["stat_pairs"], sp, rtol=1e-12, atol=0)
         else:
             assert got["pairs"].shape[0] == 0
+
+
+def test_sl_prefilter_reproduces_the_reference_held_matrix(pb):
+    """The authors' own SL_filter.R output (filter_matrix_main0.05_Zeo: 11,396 of 28,220 markers kept for 3,844 strains,
+    tests/golden/make_sl_golden.py) from the device: identical kept set, statistics to 1e-12."""
+    from conftest import golden
+    g = golden("sl_filter_zeo.npz")
+    n, k = int(g["n"]), int(g["k"])
+    X = np.unpackbits(g["bits"], axis=1)[:, :k].astype(np.float64) * 2 - 1
+    got = pb.SLFilter(X, g["y"], float(g["tau_main"]), 0.0, "no")
+    assert np.array_equal(got["main"] - 1, g["kept"]) and got["main"].size == 11396
+    assert np.allclose(got["stat_main"], g["stat"], rtol=1e-12, atol=0)

@@ -184,3 +184,38 @@ def test_sl_filter_restatement_matches_correlation(bundled):
     # every candidate not returned is below its threshold
     allm = np.array([abs(np.corrcoef(X[:, c], y)[0, 1]) * (n - 1) / n for c in range(X.shape[1])])
     assert set(np.nonzero(allm > 0.05)[0] + 1) == set(main.tolist())
+
+
+def test_sl_filter_restatement_reproduces_reference_held_matrix():
+    """oracle/rlayer.py:sl_filter against the kept set of the authors' own filter output (tests/golden/make_sl_golden.py
+    verified, where the reference checkout exists, that these are exactly the columns of filter_matrix_main0.05_Zeo)."""
+    from conftest import golden
+    g = golden("sl_filter_zeo.npz")
+    k = int(g["k"])
+    X = np.unpackbits(g["bits"], axis=1)[:, :k].astype(np.float64) * 2 - 1
+    main, _pairs, stat, _ = R.sl_filter(X, g["y"], float(g["tau_main"]), 0.0, False)
+    assert np.array_equal(main - 1, g["kept"]) and np.allclose(stat, g["stat"], rtol=1e-13, atol=0)
+
+
+def test_streaming_identity(bundled, built):
+    """The identity behind the streaming kernels (pareben_b200/csrc/stream.cuh): recomputing S_in / Q_in from the active set
+    after every action -- with the beta of the last FullStat and the ghost term of deleted bases -- reproduces the
+    reference's incrementally corrected arrays: same supports, results equal far below the 1e-8 parity tolerance."""
+    lib = R.fit_lib("port")
+    X, y = bundled["BASIS"].astype(float), bundled["y"].astype(float)
+    cases = [(X[:300, 100:140], y[:300], True, 0.01, 1.0), (X[:300, 100:140], y[:300], True, 0.02, 0.5),
+             (X[:400], y[:400], False, 0.05, 0.5), (X[:400], y[:400], False, 0.02, 1.0)]
+    biggest = 0
+    try:
+        for Xs, ys, epis, lam, al in cases:
+            lib.lib.oracle_set_fresh_statistics(0)
+            a = R.eb_elastic_net_gaussian(Xs, ys, lam, al, epis, lib)
+            lib.lib.oracle_set_fresh_statistics(1)
+            b = R.eb_elastic_net_gaussian(Xs, ys, lam, al, epis, lib)
+            assert np.array_equal(a.raw_beta[:, 2] != 0, b.raw_beta[:, 2] != 0)
+            biggest = max(biggest, a.weight.shape[0])
+            assert np.allclose(a.raw_beta[:, 2:4], b.raw_beta[:, 2:4], rtol=1e-9, atol=1e-14)
+            assert abs(a.intercept[0] - b.intercept[0]) <= 1e-10 * abs(a.intercept[0]) and abs(a.resid_var - b.resid_var) <= 1e-9 * a.resid_var
+    finally:
+        lib.lib.oracle_set_fresh_statistics(0)
+    assert biggest >= 20                      # the cases do exercise adds, deletes and re-estimates
