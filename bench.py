@@ -240,11 +240,11 @@ def run_gpu(args):
         n_grid = grid["alpha"].size
         mine = pb.shard_plan(grid["lambda"], n_folds, rank, world)
         f_vec = (mine % n_folds + 1).astype(np.int32); a_vec = grid["alpha"][mine // n_folds]; l_vec = grid["lambda"][mine // n_folds]
-        for _ in range(warmup):
+        if sampler:
+            sampler.start()                    # nvidia-smi needs a moment to deliver its first sample: started before the warm-up,
+        for _ in range(warmup):                # read after the timed steps (same kernel, same load throughout)
             prob.run_fits(f_vec, a_vec, l_vec)
         barrier()
-        if sampler:
-            sampler.start()
         ms_steps, fl_steps, wall0 = [], [], time.perf_counter()
         for _ in range(steps):
             flush.zero_()                      # L2 flush between timed iterations

@@ -88,11 +88,21 @@ static int bspd_inverse(double *a, int n)
 
 static void sigmoid_vec(double *y, const double *eta, int n) { for (int i = 0; i < n; i++) y[i] = 1 / (1 + exp(-eta[i])); }
 
+/* Test switch (tests/test_oracle.py::test_binomial_irls_accept_reject_depends_on_summation_order): sum the data error
+ * over the rows in DESCENDING order.  Mathematically the same number; it differs from the reference's ascending sum by
+ * rounding (~1e-14), which is enough to flip the IRLS accept test `newTotalError >= errorLog` (NEmainEff.c:1991) on steps
+ * whose true decrease is below that -- the fit then keeps an iterate with |g| just above 1e-6 instead of just below, and
+ * its weights move by ~1e-8.  Any implementation that does not add these N terms in exactly the reference's order (a
+ * parallel reduction cannot) inherits that sensitivity. */
+static int g_reverse_error_sum = 0;
+void oracle_set_reverse_error_sum(int on) { g_reverse_error_sum = on; }
+
 static double data_error(double *y, const double *eta, const double *t, int n)
 {   /* NEmainEff.c:2013-2025 */
     double e = 0;
     sigmoid_vec(y, eta, n);
-    for (int i = 0; i < n; i++) {
+    for (int k = 0; k < n; k++) {
+        const int i = g_reverse_error_sum ? n - 1 - k : k;
         if (y[i] != 0) e = e - t[i] * log(y[i]);
         if (y[i] != 1) e = e - (1 - t[i]) * log(1 - y[i]);
     }

@@ -6,6 +6,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 # optional: python scripts/make_profiles.py r01 <report.ncu-rep> <suffix> "<workload text>"  -> only profiles/<tag>_fit_kernel_<suffix>_ncu.md
 ALT = sys.argv[2:5] if len(sys.argv) >= 5 else None
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROUND = f"Round {int(tag[1:])}" if tag[1:].isdigit() else tag
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
@@ -19,7 +20,7 @@ if not ALT:
         agg[name][0] += 1; agg[name][1] += float(r[iv]) / 1e6
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, f"{tag}_launches.md"), "w") as f:
-        f.write(f"# Round 1 -- ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu`\n\n"
+        f.write(f"# {ROUND} -- ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu`\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv` (raw: `" + f"{tag}_launches_bench_steps2.csv`). "
                 "Per-launch times are cold-cache and serialised: compare shares.\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
         for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -45,7 +46,10 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_active.avg", "sm__cycles_elapsed.avg",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum",
+        "l1tex__t_requests_pipe_lsu_mem_local_op_st.sum"]
+h = [x.split(".TriageCompute.")[-1] if ".TriageCompute." in x else x for x in h]
 val = {k: (v[h.index(k)], u[h.index(k)]) for k in want if k in h}
 def num(k):
     x, un = val[k]; x = float(x.replace(",", ""))
@@ -62,7 +66,7 @@ def func_starts(path):
         m = re.match(r"^(?:__device__|static __device__)\s+(?:inline\s+)?[\w:<> \*&]+?\s+(\w+)\s*\(", ln)
         if m: out.append((i, m.group(1)))
     return out
-starts = {f: func_starts(os.path.join(ROOT, "pareben_b200", "csrc", f)) for f in ("gauss_fit.cuh", "binom_fit.cuh", "common.cuh", "fit_kernel.cuh")}
+starts = {f: func_starts(os.path.join(ROOT, "pareben_b200", "csrc", f)) for f in ("gauss_fit.cuh", "binom_fit.cuh", "common.cuh", "fit_kernel.cuh", "stream_scan.cuh", "stream_fit.cuh", "stream.cuh")}
 def region(f, line):
     best = f"{f}:(top)"
     for ln, nm in starts.get(f, []):
@@ -98,10 +102,10 @@ except OSError: pass
 out_md = os.path.join(P, f"{tag}_fit_kernel_{ALT[1]}_ncu.md" if ALT else f"{tag}_fit_kernel_ncu.md")
 with open(out_md, "w") as f:
     if ALT:
-        f.write(f"# Round 1 -- ncu `--set full` of the fit kernel: {ALT[2]}\n\n| metric | value | unit |\n|---|---|---|\n")
+        f.write(f"# {ROUND} -- ncu `--set full`: {ALT[2]}\n\n| metric | value | unit |\n|---|---|---|\n")
         alg = None
     else:
-        f.write("# Round 1 -- ncu `--set full` of the fit kernel on the bench workload\n\n"
+        f.write(f"# {ROUND} -- ncu `--set full` of the fit kernel on the bench workload\n\n"
             "Command (on the B200 box, after the same command exited 0 without ncu): `ncu --set full --clock-control none --import-source on "
             "-k regex:eben_fit -s 1 -c 1 python scripts/profile_case.py binomial 2000`  \n"
             "Workload: config 2, all 2,000 fits, ONE launch of `eben_fit_kernel<EPIS=0,BINOMIAL=1>` (hybrid kernel: DMMA contraction fed by a cp.async ring, "

@@ -26,6 +26,20 @@ for name, X, y, nf, epis, prior, gf in cases:
     q = np.quantile(rel, [0.5, 0.9, 0.99, 1.0])
     lines.append(f"| {name} | {err.size} | {int((ns != g['n_selected']).sum())} | {int((st != 0).sum())} | "
                  f"{q[0]:.1e} | {q[1]:.1e} | {q[2]:.1e} | {q[3]:.1e} | {int((rel > 1e-8).sum())} |")
+# streaming organisation: the K = 2,000 slice of config 5 (2,001,000 candidates) against the reference's own C
+from pareben_b200.synth import config5
+g = np.load(G + "stream_k2000.npz")
+d = config5(int(g["n"]), int(g["k"]), int(g["seed"]))
+gi, fi = np.nonzero(np.isfinite(g["fold_err"]))
+pb.set_mode(pb.MODE_STREAMING)
+with pb.Problem(d["X"].astype(float), d["y"], g["fold_id"], int(g["n_folds"]), epis=True) as prob:
+    err, st, ns, it = prob.run_fits(fi + 1, g["alpha"][gi], g["lam"][gi])
+pb.set_mode(pb.MODE_AUTO)
+want = g["fold_err"][gi, fi]
+rel = np.abs(err - want) / np.abs(want)
+q = np.quantile(rel, [0.5, 0.9, 0.99, 1.0])
+lines.append(f"| stream_k2000_epis (streaming kernels, 2,001,000 candidates, active sets 1..{int(ns.max())}) | {err.size} | "
+             f"{int((ns != g['n_selected'][gi, fi]).sum())} | {int((st != 0).sum())} | {q[0]:.1e} | {q[1]:.1e} | {q[2]:.1e} | {q[3]:.1e} | {int((rel > 1e-8).sum())} |")
 hdr = ("| workload | fits | support-size mismatches | status != 0 | median rel | p90 | p99 | max | fits > 1e-8 |\n"
        "|---|---|---|---|---|---|---|---|---|")
 open("gpurun_out/parity.md", "w").write(hdr + "\n" + "\n".join(lines) + "\n")

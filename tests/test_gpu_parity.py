@@ -164,14 +164,22 @@ def test_config2_binomial_full_grid(pb, bundled):
     assert np.all(st == 0)
     diff = ns != g["n_selected"]
     assert diff.sum() == 0, f"{diff.sum()} of 2000 fits with a different support size"
-    # Binomial tolerance.  The reference's IRLS accepts/rejects Newton steps on `newTotalError >=
-    # errorLog` (NEmainEff.c:1991) and stops at |g| < 1e-6: near convergence the objective change of a
-    # step (~g^2/H ~ 1e-13) is below the rounding error of the objective itself (~1e-16 * 270), so
-    # the accept/reject outcome -- and with it the final weights at the 1e-8 level -- is decided by
-    # summation order.  Any re-associated implementation therefore agrees to ~1e-8, not 1e-12:
-    # bound the worst fit at 1e-7 and require the bulk to be at rounding level.
+    # Binomial tolerance.  The reference's IRLS accepts/rejects Newton steps on `newTotalError >= errorLog`
+    # (NEmainEff.c:1991) and stops at |g| < 1e-6: near convergence the objective change of a step (~g^2/H ~ 1e-13) is
+    # below the rounding error of the objective itself (~1e-16 * 270), so the outcome -- and with it the final weights at
+    # the 1e-8 level -- is decided by the ORDER in which the N log-terms are added.  This is demonstrated, not assumed:
+    # tests/test_oracle.py::test_binomial_irls_accept_reject_depends_on_summation_order reverses that one sum inside the
+    # reference's own algorithm and 13 of the 100 top-lambda fits move by up to 1.07e-8
+    # (tests/golden/make_binomial_alt_golden.py).  A parallel reduction cannot add in the reference's order, so on those
+    # rows either branch is accepted -- to 1e-11 -- and everything else must be at 1e-8 or better.
     rel = np.abs(err - g["fold_err"]) / np.abs(g["fold_err"])
-    assert rel.max() < 1e-7
+    alt = golden("config2_binomial_alt.npz")
+    rows = alt["rows"]
+    rel_alt = np.abs(err[rows] - alt["fold_err_reversed_sum"]) / np.abs(alt["fold_err_reversed_sum"])
+    assert np.minimum(rel[rows], rel_alt).max() < 1e-11
+    rest = np.ones(err.shape[0], bool); rest[rows] = False
+    assert rel[rest].max() < 1e-8
+    assert rel.max() < 2e-8
     assert np.quantile(rel, 0.99) < 1e-12
     out = pb.CrossValidate(X, y, 5, prior="binomial")
     assert abs(out["alpha.optimal"] - float(g["alpha_optimal"])) < 1e-15
