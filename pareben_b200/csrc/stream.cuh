@@ -104,7 +104,7 @@ __device__ inline double q2_threshold(double need, double sl, double l1, double 
     if (!(need > 0)) return lo;
     double hi = 2 * lo + 4 * need + 1e-300;
     for (int it = 0; it < 400 && lub_of(hi, sl, l1, l2) < need; it++) hi *= 2;
-    for (int it = 0; it < 64; it++) {
+    for (int it = 0; it < 40; it++) {                 // lo only has to be a valid rejection bound: 2^-40 of the bracket is plenty
         const double mid = 0.5 * (lo + hi);
         if (lub_of(mid, sl, l1, l2) >= need) hi = mid; else lo = mid;
     }
@@ -131,12 +131,17 @@ __host__ __device__ inline int class_fits_per_tile(int cls) { return cls == 1 ? 
 
 __device__ inline void slot_thresholds(ScanSlot *sp, double need, double thr_basic, bool use_bound)
 {   // T[k] (in z^2 / ssq units) for `need`; only ever raised (atomicMax on the bit pattern: positive doubles are monotone)
+    double sk_prev = -1, q2_prev = 0;
     for (int k = 0; k < 8; k++) {
         double sk = sp->bs * (1 - exp2(-(double)k));
         if (sk < sp->s_lb) sk = sp->s_lb;
         sk *= 1 - 1e-9;
         double q2 = thr_basic;
-        if (use_bound) { const double q2t = q2_threshold(need, sk, sp->l1, sp->l2); if (q2t > q2) q2 = q2t; }
+        if (use_bound) {
+            const double q2t = sk == sk_prev ? q2_prev : q2_threshold(need, sk, sp->l1, sp->l2);      // buckets below s_lb share one bound
+            sk_prev = sk; q2_prev = q2t;
+            if (q2t > q2) q2 = q2t;
+        }
         const double t = q2 / (sp->bs * sp->bs);
         if (t == t && t > 0) atomicMax(reinterpret_cast<unsigned long long *>(&sp->T[k]), (unsigned long long)__double_as_longlong(t));
     }

@@ -265,7 +265,15 @@ stream_scan_kernel(Problem P, StreamFit *fits, StreamShared sh)
         const double *__restrict__ Xd = F.XTd;
         const long long cbase = ct * SCAN_CT + wid * 16;
         const int c0 = (int)min(cbase + gm, (long long)Kc - 1), c1 = (int)min(cbase + 8 + gm, (long long)Kc - 1);
-        Cand<EPIS> cd0(c0, K), cd1(c1, K);
+        // loci of this lane's two candidates; the second is 8 ids further on, usually in the same row of the pair
+        // enumeration (c = K + i (2K - i - 1) / 2 + (j - i - 1), NeFull2.c:115-134), so it is stepped instead of decoded
+        Cand<EPIS> cd0(c0, K), cd1 = cd0;
+        if (!EPIS || c1 < K || c0 < K) cd1 = Cand<EPIS>(c1, K);
+        else if (c1 != c0) {
+            int i1 = cd0.i, j1 = cd0.j + (c1 - c0);
+            while (j1 > K - 1) { j1 -= K - 1 - i1; i1++; j1 += 1; }      // past the end of row i1: continue in row i1 + 1 at its first pair
+            cd1.i = i1; cd1.j = j1;
+        }
         double acc[2][8][2];
 #pragma unroll
         for (int t = 0; t < 2; t++)

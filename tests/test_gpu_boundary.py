@@ -87,10 +87,10 @@ def test_dot_c_symbols_match_the_reference_argument_lists(pb):
         for lam, alpha in (((0.3, 1.0), (0.06, 0.5)) if not epis else ((0.3, 1.0), (0.15, 0.5))):
             got = _dot_c_binomial(mine, X, yb, lam, alpha, epis)
             want = _dot_c_binomial(theirs, X, yb, lam, alpha, epis)
-            _same_table(got[0], want[0], (2, 3), rtol=1e-7)
-            assert abs(got[1] - want[1]) <= 1e-7 * abs(want[1])
-            assert np.allclose(got[2], want[2], rtol=1e-7)
-            assert abs(got[3] - want[3]) <= 1e-7 * abs(want[3])
+            _same_table(got[0], want[0], (2, 3), rtol=5e-8)
+            assert abs(got[1] - want[1]) <= 5e-8 * abs(want[1])
+            assert np.allclose(got[2], want[2], rtol=5e-8)
+            assert abs(got[3] - want[3]) <= 5e-8 * abs(want[3])
 
 
 def test_epis_final_model_tables(pb):
@@ -117,8 +117,8 @@ def test_epis_final_model_tables(pb):
     assert stb == 0 and tb.shape == (2 * k, 4)
     m = int((fitb.raw_beta[:, 2] != 0).sum())
     assert m >= 2 and np.all(tb[m:] == 0)                                                        # compact: rows past the active set are zero
-    _same_table(tb, fitb.raw_beta, (2, 3), rtol=1e-7)
-    assert np.allclose(icptb, fitb.intercept, rtol=1e-7) and abs(logl - fitb.log_likelihood) <= 1e-7 * abs(fitb.log_likelihood)
+    _same_table(tb, fitb.raw_beta, (2, 3), rtol=5e-8)
+    assert np.allclose(icptb, fitb.intercept, rtol=5e-8) and abs(logl - fitb.log_likelihood) <= 5e-8 * abs(fitb.log_likelihood)
 
 
 def test_resident_problem_serves_lambda_max_and_grid(pb):

@@ -170,25 +170,29 @@ def test_config2_binomial_full_grid(pb, bundled):
     # the 1e-8 level -- is decided by the ORDER in which the N log-terms are added.  This is demonstrated, not assumed:
     # tests/test_oracle.py::test_binomial_irls_accept_reject_depends_on_summation_order reverses that one sum inside the
     # reference's own algorithm and 13 of the 100 top-lambda fits move by up to 1.07e-8
-    # (tests/golden/make_binomial_alt_golden.py).  A parallel reduction cannot add in the reference's order, so on those
-    # rows either branch is accepted -- to 1e-11 -- and everything else must be at 1e-8 or better.
+    # (tests/golden/make_binomial_alt_golden.py), each with a handful of such decision points.  A parallel reduction cannot
+    # add in the reference's order, so on those 100 fits the kernel is held to the demonstrated sensitivity (2e-8; measured:
+    # the same fits move, by the same 5e-9 .. 1.07e-8, most of them landing exactly on the reversed-sum branch) and
+    # everywhere else to 1e-9 (measured 1.6e-10).
     rel = np.abs(err - g["fold_err"]) / np.abs(g["fold_err"])
     alt = golden("config2_binomial_alt.npz")
     rows = alt["rows"]
     rel_alt = np.abs(err[rows] - alt["fold_err_reversed_sum"]) / np.abs(alt["fold_err_reversed_sum"])
-    assert np.minimum(rel[rows], rel_alt).max() < 1e-11
+    assert rel[rows].max() < 2e-8
+    moved = np.abs(alt["fold_err_reversed_sum"] - g["fold_err"][rows]) / np.abs(g["fold_err"][rows]) > 1e-10
+    assert np.all(rel[rows][~moved] < 1e-9), "a fit the summation order does not move must agree tightly"
+    assert (np.minimum(rel[rows], rel_alt) < 1e-10).mean() > 0.95
     rest = np.ones(err.shape[0], bool); rest[rows] = False
-    assert rel[rest].max() < 1e-8
-    assert rel.max() < 2e-8
+    assert rel[rest].max() < 1e-9
     assert np.quantile(rel, 0.99) < 1e-12
     out = pb.CrossValidate(X, y, 5, prior="binomial")
     assert abs(out["alpha.optimal"] - float(g["alpha_optimal"])) < 1e-15
     assert abs(out["lambda.optimal"] - float(g["lambda_optimal"])) <= 1e-13 * float(g["lambda_optimal"])
-    assert _rel(out["Results.Summary"]["Likelihood"], g["summary_likelihood"]) < 1e-7
+    assert _rel(out["Results.Summary"]["Likelihood"], g["summary_likelihood"]) < 2e-8
     loc = pb.CrossValidate(X, y, 5, foldId=g["fold_id"], prior="binomial", search="local")
     want = R.local_search_replay(g["grid_alpha"], g["grid_lambda"], -g["fold_err"])
     assert loc["alpha.optimal"] == want[1] and abs(loc["lambda.optimal"] - want[2]) <= 1e-13 * want[2]
-    assert np.allclose(loc["fullCV"][:, :3], want[3][:, :3], rtol=1e-7, atol=0)
+    assert np.allclose(loc["fullCV"][:, :3], want[3][:, :3], rtol=2e-8, atol=0)
     assert np.allclose(loc["fullCV"][:, 3], want[3][:, 3], rtol=1e-4, atol=0)      # SE = sd/sqrt(n): differences of near-equal numbers
 
 
@@ -212,8 +216,8 @@ def test_binomial_final_model_live(pb, bundled):
         got = pb.EBelasticNet_Binomial(X, y, lam, a)
         assert got["weight"].shape == want.weight.shape
         assert np.array_equal(got["weight"][:, :2], want.weight[:, :2])
-        assert np.allclose(got["weight"][:, 2:4], want.weight[:, 2:4], rtol=1e-7, atol=1e-12)
-        assert np.allclose(got["Intercept"], want.intercept, rtol=1e-7)
+        assert np.allclose(got["weight"][:, 2:4], want.weight[:, 2:4], rtol=5e-8, atol=1e-12)
+        assert np.allclose(got["Intercept"], want.intercept, rtol=5e-8)
         assert abs(got["logLikelihood"] - want.log_likelihood) <= 1e-8 * abs(want.log_likelihood)
 
 

@@ -8,8 +8,9 @@ inputs generated here.  Scaled-down stand-ins for BASELINE configs 3-5:
     finishes in seconds), Gaussian and binomial,
   * a real-valued (non-genotype) design, which takes the f64 operand path of the tensor-core
     contraction instead of the int8 one.
-Tolerances as in test_gpu_parity.py: 1e-8 relative on Gaussian fold errors, 1e-7 on binomial
-ones (see the note there), support sizes identical.
+Tolerances as in test_gpu_parity.py: 1e-8 relative on Gaussian fold errors, 5e-8 on binomial
+ones (the IRLS accept test depends on the summation order of the build at the 1e-8 level: demonstrated in
+tests/test_oracle.py::test_binomial_irls_accept_reject_depends_on_summation_order), support sizes identical.
 """
 import numpy as np
 import pytest
@@ -83,7 +84,7 @@ def test_epis_binomial_thousands_of_pairs(pb):
     eta = 1.2 * X[:, 5] - 1.0 * X[:, 17] + 1.5 * X[:, 2] * X[:, 30]
     y = (rng.random(n) < 1 / (1 + np.exp(-eta))).astype(float)
     lam = np.array([0.5, 0.12]); alpha = np.array([1.0, 0.4])
-    _check(pb, X, y, 2, lam, alpha, True, "binomial", 1e-7)
+    _check(pb, X, y, 2, lam, alpha, True, "binomial", 5e-8)
 
 
 def test_real_valued_design_uses_f64_operands(pb):
@@ -97,7 +98,7 @@ def test_real_valued_design_uses_f64_operands(pb):
     m = _check(pb, X, y, 3, lam, alpha, False, "gaussian", 1e-8)
     assert m > 4            # more than SIMT_R_MAX right-hand sides: the tensor-core path ran
     yb = (rng.random(n) < 1 / (1 + np.exp(-(X[:, 0] - X[:, 1] + 0.5 * X[:, 2])))).astype(float)
-    _check(pb, X, yb, 3, np.array([0.3, 0.05]), np.array([1.0, 0.3]), False, "binomial", 1e-7)
+    _check(pb, X, yb, 3, np.array([0.3, 0.05]), np.array([1.0, 0.3]), False, "binomial", 5e-8)
     # pairs of real-valued loci
     _check(pb, X[:, :14], y, 2, np.array([0.8, 0.1]), np.array([0.9, 0.2]), True, "gaussian", 1e-8)
 
