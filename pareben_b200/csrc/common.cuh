@@ -43,6 +43,10 @@ struct FoldData {
     const double *XTd;
     int ldt;
     int ntr, nte;
+    // Gaussian fits, "Gram" organisation (null otherwise): C[p][c] = x_c' phi_p / s_c for EVERY candidate p, i.e. the
+    // row the reference's CacheBP* (MainEff.c:1144-1201) would compute for basis p.  It depends on the fold only -- not
+    // on alpha, lambda or the solver's state -- so it is built once per fold (fold_gram_kernel) and shared by all fits.
+    double *C;
 };
 
 struct Problem {

@@ -131,6 +131,66 @@ eben_fit_kernel(Problem P, Variant v, const FitTask *__restrict__ tasks, int n_t
 }
 
 
+// Gram organisation of the Gaussian fits (FoldData::C): row p of C is the cache row x_c' phi_p / s_c of candidate p as
+// basis, for every candidate -- what CacheBP* (MainEff.c:1144-1201) and ActionAdd* (:1608-1618) compute again for every
+// basis of every fit although it depends on the fold alone.  One launch builds the rows of all listed folds: a block
+// takes 32 candidates at a time, writes their normalised columns (exactly the column an add would build, :1590-1606 /
+// NeFull2.c:277-290) into its own slab's PHI and runs the same tensor-core contraction a fit runs at the top of an outer
+// iteration, with C's rows as destinations.  2 N Kc^2 flops per fold, once per problem.
+constexpr int GRAM_CHUNK = 8 * NT_MAX;
+
+template <bool EPIS>
+__global__ void __launch_bounds__(FIT_THREADS, PAREBEN_MIN_BLOCKS)
+fold_gram_kernel(Problem P, const int *__restrict__ fold_list, int n_fold_list, char *slabs, size_t slab_stride, int *next_item)
+{
+    extern __shared__ __align__(32) double s_buf[];
+    __shared__ int s_item;
+    const int K = P.K, Kc = P.Kc, T = blockDim.x;
+    const int chunks = (Kc + GRAM_CHUNK - 1) / GRAM_CHUNK;
+    const int n_items = chunks * n_fold_list;
+    Slab s = carve_slab(slabs + (size_t)blockIdx.x * slab_stride, P.cap, P.nmax, Kc);
+    const int rpb = min(GRAM_CHUNK, P.cap);            // right-hand sides per contraction: the slab's PHI holds `cap` columns
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(next_item, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        const FoldData F = P.folds[fold_list[item / chunks]];
+        const int N = F.ntr, LD = phi_ld(N);
+        const int p_begin = (item % chunks) * GRAM_CHUNK, p_end = min(p_begin + GRAM_CHUNK, Kc);
+        for (int p0 = p_begin; p0 < p_end; p0 += rpb) {
+            const int R = min(rpb, p_end - p0);
+            __syncthreads();
+            for (int r = threadIdx.x & 31; r < R; r += 32) {             // a lane owns a column: one decode, coalesced row reads
+                Cand<EPIS> cd(p0 + r, K);
+                const double sc_p = F.scale[p0 + r], isc = 1 / sc_p;
+                const bool pair = cd.i != cd.j;
+                double *col = s.phi + (size_t)r * LD;
+                for (int h = threadIdx.x >> 5; h < LD; h += T >> 5) {
+                    double val = 0.0;
+                    if (h < N) { const double x = cd.at(F.Xtr + (size_t)h * K); val = pair ? x / sc_p : x * isc; }
+                    col[h] = val;
+                }
+            }
+            __syncthreads();
+            contract_x<EPIS>(F, K, Kc, R, R,
+                [&](int r) -> const double * { return s.phi + (size_t)r * LD; },
+                [&](int r, bool &dv) -> double * { dv = true; return F.C + (size_t)(p0 + r) * Kc; }, s_buf);
+        }
+    }
+}
+
+template <bool EPIS>
+inline cudaError_t launch_gram_variant(int grid, int threads, cudaStream_t stream, const Problem &P, const int *fold_list,
+                                       int n_fold_list, char *slabs, size_t slab_stride, int *next_item)
+{
+    cudaError_t e = cudaFuncSetAttribute(fold_gram_kernel<EPIS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_BUF_BYTES);
+    if (e != cudaSuccess) return e;
+    fold_gram_kernel<EPIS><<<grid, threads, S_BUF_BYTES, stream>>>(P, fold_list, n_fold_list, slabs, slab_stride, next_item);
+    return cudaGetLastError();
+}
+
 template <bool EPIS, bool BINOMIAL>
 inline cudaError_t launch_fit_variant(int grid, int threads, cudaStream_t stream, const Problem &P, const Variant &v,
                                       const FitTask *tasks, int n_tasks, const Sched &sched, char *slabs, size_t slab_stride,
@@ -179,4 +239,11 @@ inline void timing_variant(unsigned long long *cycles_calls, int reset, unsigned
     cudaError_t occupancy_##NAME(int *blocks_per_sm, int threads) { return occupancy_variant<EPIS, BINOMIAL>(blocks_per_sm, threads); } \
     void timing_##NAME(unsigned long long *cc, int reset, unsigned long long *t0, unsigned long long *t1, int *block, int n) \
     { timing_variant(cc, reset, t0, t1, block, n); }                                                                      \
+    }
+
+#define PAREBEN_DEFINE_GRAM(NAME, EPIS)                                                                                   \
+    namespace pareben {                                                                                                   \
+    cudaError_t launch_gram_##NAME(int grid, int threads, cudaStream_t stream, const Problem &P, const int *fold_list,   \
+                                   int n_fold_list, char *slabs, size_t slab_stride, int *next_item)                      \
+    { return launch_gram_variant<EPIS>(grid, threads, stream, P, fold_list, n_fold_list, slabs, slab_stride, next_item); } \
     }

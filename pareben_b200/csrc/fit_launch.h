@@ -18,4 +18,10 @@ PAREBEN_DECLARE_VARIANT(ge)   // Gaussian, Epis
 PAREBEN_DECLARE_VARIANT(bm)   // binomial, main effects
 PAREBEN_DECLARE_VARIANT(be)   // binomial, Epis
 
+// Gaussian only: build FoldData::C for the listed folds (fold_gram_kernel, fit_kernel.cuh)
+cudaError_t launch_gram_gm(int grid, int threads, cudaStream_t stream, const Problem &P, const int *fold_list, int n_fold_list,
+                           char *slabs, size_t slab_stride, int *next_item);
+cudaError_t launch_gram_ge(int grid, int threads, cudaStream_t stream, const Problem &P, const int *fold_list, int n_fold_list,
+                           char *slabs, size_t slab_stride, int *next_item);
+
 }  // namespace pareben

@@ -1376,6 +1376,11 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
     const int lane_ = threadIdx.x & 31, wid_ = threadIdx.x >> 5, nw_ = T >> 5;
     const double *X = F.Xtr, *y = F.ytr, *scale = F.scale;
     GaussState g; g.M = 1; g.n_unused = 0; g.cap = cap; g.beta = 0; g.status = 0; g.flops = 0;
+    // Gram organisation: the cache row of basis p is row p of the fold's shared matrix C (FoldData::C), so the cache is
+    // never computed or stored per fit -- `grow[j]` simply holds the candidate id of active slot j, and every reader of
+    // the cache (quadratic forms, S/Q corrections) streams rows that all fits of the fold share in L2.
+    const bool gram = F.C != nullptr;
+    if (gram) s.G = F.C;
 
     for (int j = threadIdx.x; j < cap; j += T) { s.grow[j] = j; s.alpha[j] = 0; s.mu[j] = 0; }
     double b = 0;
@@ -1424,11 +1429,16 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
         // candidate cache G = PHI'X/s and xt = X't/s  (CacheBP*, :1144-1201)
         {
             const int M = g.M;
-            contract_x<EPIS>(F, K, Kc, M + 1, M,
-                [&](int r) -> const double * { return r < M ? s.phi + (size_t)r * LD : s.t; },
-                [&](int r, bool &dv) -> double * { dv = true; return r < M ? s.G + (size_t)s.grow[r] * Kc : s.xt; },
-                sV);
-            if (threadIdx.x == 0) g.flops += 2.0 * N * (double)Kc * (M + 1);
+            if (gram)       // only xt depends on the fit (t = y - b); the M cache rows are rows of C
+                contract_x<EPIS>(F, K, Kc, 1, 0,
+                    [&](int) -> const double * { return s.t; },
+                    [&](int, bool &dv) -> double * { dv = true; return s.xt; }, sV);
+            else
+                contract_x<EPIS>(F, K, Kc, M + 1, M,
+                    [&](int r) -> const double * { return r < M ? s.phi + (size_t)r * LD : s.t; },
+                    [&](int r, bool &dv) -> double * { dv = true; return r < M ? s.G + (size_t)s.grow[r] * Kc : s.xt; },
+                    sV);
+            if (threadIdx.x == 0) g.flops += 2.0 * N * (double)Kc * (M + 1);     // the SURVEY 8d model of this step (gram: only 2 N Kc executed)
         }
         int i_iter = 0;
         full_stat(s, g, N, Kc, iter == 1, sc);
@@ -1511,7 +1521,9 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                                 }
                             }
                             __syncthreads();
-                            const int grow_new = s.grow[M];
+                            const int grow_new = gram ? nu : s.grow[M];
+                            if (gram) { if (threadIdx.x == 0) s.grow[M] = nu; }          // row nu of C is the new cache row
+                            else
                             contract_x<EPIS>(F, K, Kc, 1, 0,
                                 [&](int) -> const double * { return s.phinew; },
                                 [&](int, bool &dv) -> double * { dv = true; return s.G + (size_t)grow_new * Kc; }, sV);

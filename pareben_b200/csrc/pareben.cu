@@ -291,6 +291,9 @@ struct pareben_problem {
     int threads = 256;                   // threads per block actually launched
     double last_flops = 0, last_ms = 0; int last_launches = 0;
     bool streaming = false;              // fits run through the streaming kernels (no per-candidate arrays anywhere)
+    // Gram organisation (Gaussian, cached kernels): FoldData::C per fold, built on first use and kept with the problem
+    int gram_state = 0;                  // 0 = undecided, 1 = in use, -1 = refused (memory or too little work)
+    double gram_ms = 0; int gram_launches = 0;      // time / launches spent building C in the last run_fits call
     double last_scan_ms = 0, last_scan_flops = 0; int last_scan_launches = 0, last_rounds = 0;
 
     template <class T> T *dalloc(size_t n)
@@ -382,6 +385,65 @@ static void ensure_slabs(pareben_problem *p)
         CU(malloc_retry(p->device, &q, p->slab_total));
         p->d_slabs = (char *)q;
     }
+}
+
+// Gram organisation of the Gaussian fits (fold_gram_kernel, fit_kernel.cuh).  C costs 8 Kc^2 bytes and 2 N Kc^2 flops per
+// fold; a fit then never contracts the training matrix against a basis column again.  Worth it when the call has enough
+// work to amortise it (a fit contracts ~ (outer iterations) x (active set) + (adds) columns, hundreds for a grid point)
+// and the matrices fit beside the work slabs.  PAREBEN_GRAM=0 / 1 overrides the work test (never the memory test).
+// Once built, C stays with the problem handle: BuildGrid -> cv_grid -> LocalSearch share it.  Throws like CU().
+static void ensure_gram(pareben_problem *p, int n_fits, const int *fold)
+{
+    p->gram_ms = 0; p->gram_launches = 0;
+    if (p->prior != PAREBEN_GAUSSIAN || p->streaming) return;
+    const char *env = getenv("PAREBEN_GRAM");
+    const int forced = env ? atoi(env) : -1;
+    if (forced == 0) {
+        if (p->gram_state == 1) {       // drop the pointers (the buffers stay in p->allocs until the problem is destroyed)
+            for (FoldData &F : p->h_folds) F.C = nullptr;
+            CU(cudaMemcpyAsync(p->d_folds, p->h_folds.data(), sizeof(FoldData) * p->h_folds.size(), cudaMemcpyHostToDevice, p->stream));
+            p->gram_state = 0;
+        }
+        return;
+    }
+    if (p->gram_state < 0) return;
+    std::vector<int> need;              // folds of this call whose C does not exist yet
+    {
+        std::vector<char> seen(p->h_folds.size(), 0);
+        for (int i = 0; i < n_fits; i++) if (!seen[fold[i]]) { seen[fold[i]] = 1; if (!p->h_folds[fold[i]].C) need.push_back(fold[i]); }
+    }
+    if (need.empty()) return;
+    const size_t bytes_per_fold = ((size_t)p->kc * p->kc * sizeof(double) + 255) & ~(size_t)255;
+    if (p->gram_state == 0) {
+        int n_distinct = 0;
+        { std::vector<char> seen(p->h_folds.size(), 0); for (int i = 0; i < n_fits; i++) if (!seen[fold[i]]) { seen[fold[i]] = 1; n_distinct++; } }
+        if (forced != 1 && (double)n_distinct * p->kc > 512.0 * n_fits) return;      // too little work in this call: decide again next time
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        free_b += pool_parked(p->device);
+        const size_t all_folds = bytes_per_fold * (size_t)std::max(1, p->n_folds);
+        if (all_folds > free_b / 2) { p->gram_state = -1; return; }
+        p->gram_state = 1;
+    }
+    for (int f : need) p->h_folds[f].C = p->dalloc<double>(bytes_per_fold / sizeof(double));
+    int *d_list = p->dalloc<int>(need.size() + 1);           // fold list + the work counter (small, kept with the problem)
+    std::vector<int> h_list(need);
+    h_list.push_back(0);
+    CU(cudaMemcpyAsync(d_list, h_list.data(), sizeof(int) * h_list.size(), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->d_folds, p->h_folds.data(), sizeof(FoldData) * p->h_folds.size(), cudaMemcpyHostToDevice, p->stream));
+    Problem P;
+    P.N = p->n; P.K = p->k; P.Kc = p->kc; P.n_folds = p->n_folds; P.epis = p->epis; P.prior = p->prior;
+    P.cap = p->cap; P.nmax = p->nmax; P.folds = p->d_folds;
+    const int chunks = (p->kc + 31) / 32;
+    const int grid = (int)std::min<long long>(p->n_slabs, (long long)chunks * (long long)need.size());
+    CU(cudaEventRecord(p->ev0, p->stream));
+    CU((p->epis ? launch_gram_ge : launch_gram_gm)(grid, p->threads, p->stream, P, d_list, (int)need.size(), p->d_slabs, p->slab_stride,
+                                                   d_list + need.size()));
+    CU(cudaEventRecord(p->ev1, p->stream));
+    CU(cudaStreamSynchronize(p->stream));       // h_list goes out of scope; and the build time is reported
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    p->gram_ms = ms; p->gram_launches = 1;
 }
 
 extern "C" int pareben_device_count(void)
@@ -712,6 +774,10 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
     try {
         CU(cudaSetDevice(p->device));
         ensure_slabs(p);
+        for (int i = 0; i < n_fits; i++)
+            if (fold[i] < 0 || fold[i] > p->n_folds || (p->n_folds > 0 && fold[i] == 0) || !p->h_folds[fold[i]].Xtr)
+                return fail(PAREBEN_EINVAL, "pareben_run_fits: fold label not available in this problem");
+        ensure_gram(p, n_fits, fold);
         std::vector<FitTask> tasks(n_fits);
         // groups: fits that share (alpha, lambda) -- one row of the reference's ParameterGrid -- differ only in the fold
         // and cost about the same; the device scheduler prices a group by its first finished fit (fit_kernel.cuh)
@@ -781,7 +847,7 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
         CU(cudaStreamSynchronize(p->stream));
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
-        p->last_ms = ms; p->last_flops = h_flops; p->last_launches = 1;
+        p->last_ms = ms + p->gram_ms; p->last_flops = h_flops; p->last_launches = 1 + p->gram_launches;      // a call that had to build C pays for it
         for (int i = 0; i < n_fits; i++) {
             if (fold_err) fold_err[i] = h_err[i];
             if (status) status[i] = h_ints[i];
