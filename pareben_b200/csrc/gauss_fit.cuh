@@ -527,9 +527,11 @@ __device__ inline void quad_forms_simt(const Slab &s, const double *sigma, doubl
     double *sigp = (M * ldp <= 4096) ? smem : sigp_global;
     size_t *rowoff = reinterpret_cast<size_t *>(smem + 4096);          // G row offsets: no dependent index load in the hot loop
     __syncthreads();
+    // SIGMA is symmetric: g'SIGMA g = sum_p g_p (SIGMA_pp g_p + 2 sum_{j<p} SIGMA_pj g_j), so only the lower triangle is
+    // multiplied (off-diagonal entries doubled -- exact -- and the upper triangle of the copy zero): half the FMAs
     for (int idx = threadIdx.x; idx < M * ldp; idx += T) {
         const int j = idx / ldp, p = idx - j * ldp;
-        sigp[idx] = p < M ? sigma[p * M + j] : 0.0;
+        sigp[idx] = (p < M && j <= p) ? (j < p ? 2.0 * sigma[p * M + j] : sigma[p * M + j]) : 0.0;
     }
     const bool off_smem = M <= 1040;
     if (off_smem) for (int j = threadIdx.x; j < M; j += T) rowoff[j] = (size_t)s.grow[j] * Kc;
@@ -545,7 +547,8 @@ __device__ inline void quad_forms_simt(const Slab &s, const double *sigma, doubl
             double za[PW], zb[PW];
 #pragma unroll
             for (int q = 0; q < PW; q++) { za[q] = 0.0; zb[q] = 0.0; }
-            for (int j = 0; j < M; j += 4) {
+            const int jend = min(M, p0 + PW);             // rows j > p hold zeros
+            for (int j = 0; j < jend; j += 4) {
                 double ga[4], gb[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -554,7 +557,7 @@ __device__ inline void quad_forms_simt(const Slab &s, const double *sigma, doubl
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (j + u < M) {
+                    if (j + u < jend) {
                         const double4 *row = reinterpret_cast<const double4 *>(sigp + (size_t)(j + u) * ldp + p0);
 #pragma unroll
                         for (int q4 = 0; q4 < PW / 4; q4++) {
@@ -599,7 +602,8 @@ __device__ inline void quad_chunk(const double *__restrict__ G, const size_t *ro
 {
     const int lane = threadIdx.x & 31;
     const int gm = lane >> 2, gk = lane & 3;
-    const int nstage = (M + QT - 1) / QT;
+    const int jlim = min(M, p0 + 8 * NT);                   // lower triangle only (see quad_forms_mma): rows j > p hold zeros
+    const int nstage = (jlim + QT - 1) / QT;
     auto roff = [&](int j) -> size_t { return rowoff ? rowoff[j] : (size_t)grow[j] * Kc; };
     double acc[MT][NT][2];
 #pragma unroll
@@ -624,7 +628,7 @@ __device__ inline void quad_chunk(const double *__restrict__ G, const size_t *ro
         if (live) {
 #pragma unroll
             for (int g = 0; g < QT / 16; g++) {
-                if (st * QT + 16 * g < M) {                    // warp-uniform: groups past the last cache row are skipped
+                if (st * QT + 16 * g < jlim) {                 // warp-uniform: groups past the last contributing cache row are skipped
                     fetch(xn2, st * QT + 16 * (g + 2));
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++) {
@@ -674,16 +678,19 @@ __device__ inline void quad_forms_mma(const Slab &s, const double *sigma, double
     const bool resident = Mp <= 2 * QT;
     size_t *rowoff = M <= 784 ? reinterpret_cast<size_t *>(smem + 2 * QT * LDS_V) : nullptr;
     __syncthreads();
-    // zero-padded copy sigp[j][p] = SIGMA(p, j): straight into the shared tile layout when resident
+    // zero-padded copy sigp[j][p] of SIGMA's lower triangle, off-diagonal entries doubled (exact): SIGMA is symmetric, so
+    // g'SIGMA g = sum_p g_p (SIGMA_pp g_p + 2 sum_{j<p} SIGMA_pj g_j) and a chunk of columns p only needs the cache rows
+    // j <= p -- half the DMMAs.  Straight into the shared tile layout when resident.
+    auto tri = [&](int j, int p) { return (p < M && j <= p) ? (j < p ? 2.0 * sigma[p * M + j] : sigma[p * M + j]) : 0.0; };
     if (resident) {
         for (int idx = threadIdx.x; idx < Mp * ldp; idx += T) {
             const int j = idx / ldp, p = idx - j * ldp;
-            smem[j * LDS_V + p] = (j < M && p < M) ? sigma[p * M + j] : 0.0;
+            smem[j * LDS_V + p] = tri(j, p);
         }
     } else {
         for (int idx = threadIdx.x; idx < Mp * ldp; idx += T) {
             const int j = idx / ldp, p = idx - j * ldp;
-            sigp_global[idx] = (j < M && p < M) ? sigma[p * M + j] : 0.0;
+            sigp_global[idx] = tri(j, p);
         }
     }
     if (rowoff) for (int j = threadIdx.x; j < M; j += T) rowoff[j] = (size_t)s.grow[j] * Kc;
@@ -877,26 +884,46 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
         }
         if (!ok) break;
         __syncthreads();
-        // phase B: rank-nb update of the lower triangle, mirrored
-        for (int t = wid; t < ntile; t += nw) {
-            int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-            while (ti * (ti + 1) / 2 > t) ti--;
-            while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-            const int tj = t - ti * (ti + 1) / 2;
-            const int i = 8 * ti + gm, j0 = 8 * tj + 2 * gk;          // this lane's elements: (i, j0) and (i, j0 + 1)
-            double c0 = (i < M && j0 < M) ? a[(size_t)j0 * M + i] : 0.0;
-            double c1 = (i < M && j0 + 1 < M) ? a[(size_t)(j0 + 1) * M + i] : 0.0;
+        // phase B: rank-nb update of the lower triangle, mirrored.  A warp works on PB tiles at a time: the tile's own
+        // entries come from L2 and a single load -> DMMA -> store chain per warp would pay that latency once per tile.
+        constexpr int PB = 4;
+        for (int tb = wid; tb < ntile; tb += nw * PB) {
+            int ti_[PB], tj_[PB];
+            double c0[PB], c1[PB];
+#pragma unroll
+            for (int u = 0; u < PB; u++) {
+                const int t = tb + u * nw;
+                int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while (ti * (ti + 1) / 2 > t) ti--;
+                while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+                ti_[u] = ti; tj_[u] = t - ti * (ti + 1) / 2;
+                const bool lv = t < ntile;
+                const int i = 8 * ti + gm, j0 = 8 * tj_[u] + 2 * gk;      // this lane's elements: (i, j0) and (i, j0 + 1)
+                c0[u] = (lv && i < M && j0 < M) ? a[(size_t)j0 * M + i] : 0.0;
+                c1[u] = (lv && i < M && j0 + 1 < M) ? a[(size_t)(j0 + 1) * M + i] : 0.0;
+            }
 #pragma unroll
             for (int ks = 0; ks < 2; ks++) {
                 if (ks < KS) {
-                    const double af = -C[(4 * ks + gk) * Mp + 8 * ti + gm];
-                    const double bf = D[(4 * ks + gk) * Mp + 8 * tj + gm];
-                    dmma(c0, c1, af, bf);
+#pragma unroll
+                    for (int u = 0; u < PB; u++) {
+                        if (tb + u * nw < ntile) {                         // warp-uniform
+                            const double af = -C[(4 * ks + gk) * Mp + 8 * ti_[u] + gm];
+                            const double bf = D[(4 * ks + gk) * Mp + 8 * tj_[u] + gm];
+                            dmma(c0[u], c1[u], af, bf);
+                        }
+                    }
                 }
             }
-            const bool diag = ti == tj;
-            if (i < M && j0 < M && (!diag || i >= j0)) { a[(size_t)j0 * M + i] = c0; a[(size_t)i * M + j0] = c0; }
-            if (i < M && j0 + 1 < M && (!diag || i >= j0 + 1)) { a[(size_t)(j0 + 1) * M + i] = c1; a[(size_t)i * M + j0 + 1] = c1; }
+#pragma unroll
+            for (int u = 0; u < PB; u++) {
+                if (tb + u * nw < ntile) {
+                    const int i = 8 * ti_[u] + gm, j0 = 8 * tj_[u] + 2 * gk;
+                    const bool diag = ti_[u] == tj_[u];
+                    if (i < M && j0 < M && (!diag || i >= j0)) { a[(size_t)j0 * M + i] = c0[u]; a[(size_t)i * M + j0] = c0[u]; }
+                    if (i < M && j0 + 1 < M && (!diag || i >= j0 + 1)) { a[(size_t)(j0 + 1) * M + i] = c1[u]; a[(size_t)i * M + j0 + 1] = c1[u]; }
+                }
+            }
         }
         __syncthreads();
         // the panel's own columns, and their mirror image: the rows of the panel's pivots
@@ -1494,11 +1521,17 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                         __syncthreads();
                         if (threadIdx.x == 0) s.alpha[jj] = new_alpha;
                         for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mujj * kappa * sj[i];
-                        for (int j = wid_; j < M; j += nw_)                      // warps own columns, lanes rows: no integer division
-                            for (int i = lane_; i < M; i += 32) {
-                                const int idx = j * M + i;
-                                s.sigma_new[idx] = s.sigma[idx] - kappa * sj[i] * sj[j];
+                        {   // (restrict: the two SIGMA buffers never alias, so the loads of an unrolled row run ahead of its stores)
+                            const double *__restrict__ sg = s.sigma; double *__restrict__ sn = s.sigma_new;
+                            for (int j = wid_; j < M; j += nw_) {                // warps own columns, lanes rows: no integer division
+                                const double kj = sg[jj * M + j];
+#pragma unroll 4
+                                for (int i = lane_; i < M; i += 32) {
+                                    const int idx = j * M + i;
+                                    sn[idx] = sg[idx] - kappa * sg[jj * M + i] * kj;
+                                }
                             }
+                        }
                         const double beta = g.beta;
                         cache_dot(s, M, Kc, sj, [&](int c, double z) {
                             const double bz = beta * z;
@@ -1550,14 +1583,21 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             for (int i = threadIdx.x; i < M; i += T) s.mu[i] += -mu_i * s.u[i];
                             if (threadIdx.x == 0) s.mu[M] = mu_i;
                             const int M1 = M + 1;
-                            for (int j = wid_; j < M1; j += nw_)
-                                for (int i = lane_; i < M1; i += 32) {
-                                    double val;
-                                    if (i < M && j < M) val = s.sigma[j * M + i] + (s_ii * s.u[i]) * s.u[j];
-                                    else if (i == M && j == M) val = s_ii;
-                                    else val = -s_ii * s.u[i < M ? i : j];
-                                    s.sigma_new[j * M1 + i] = val;
+                            {
+                                const double *__restrict__ sg = s.sigma; double *__restrict__ sn = s.sigma_new;
+                                const double *__restrict__ uu = s.u;
+                                for (int j = wid_; j < M1; j += nw_) {
+                                    const double uj = uu[min(j, M - 1)];
+#pragma unroll 4
+                                    for (int i = lane_; i < M1; i += 32) {
+                                        double val;
+                                        if (i < M && j < M) val = sg[j * M + i] + (s_ii * uu[i]) * uj;
+                                        else if (i == M && j == M) val = s_ii;
+                                        else val = -s_ii * uu[i < M ? i : j];
+                                        sn[j * M1 + i] = val;
+                                    }
                                 }
+                            }
                             const double beta = g.beta;
                             cache_dot(s, M, Kc, s.u, [&](int c, double z) {
                                 const double mci = beta * s.G[(size_t)grow_new * Kc + c] - beta * z;
@@ -1597,11 +1637,17 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                         // Schur downdate, then move the last row/column into slot jj (:1754-1776)
                         for (int i = threadIdx.x; i < M; i += T) s.colk[i] = sj[i] / sjj;      // one division per row, not per entry
                         __syncthreads();
-                        for (int j = wid_; j < lastj; j += nw_) {
-                            const int sjx = (j == jj) ? lastj : j;
-                            for (int i = lane_; i < lastj; i += 32) {
-                                const int si = (i == jj) ? lastj : i;
-                                s.sigma_new[j * lastj + i] = s.sigma[sjx * M + si] - s.colk[si] * sj[sjx];
+                        {
+                            const double *__restrict__ sg = s.sigma; double *__restrict__ sn = s.sigma_new;
+                            const double *__restrict__ ck = s.colk;
+                            for (int j = wid_; j < lastj; j += nw_) {
+                                const int sjx = (j == jj) ? lastj : j;
+                                const double sjv = sg[jj * M + sjx];
+#pragma unroll 4
+                                for (int i = lane_; i < lastj; i += 32) {
+                                    const int si = (i == jj) ? lastj : i;
+                                    sn[j * lastj + i] = sg[sjx * M + si] - ck[si] * sjv;
+                                }
                             }
                         }
                         const double beta = g.beta;

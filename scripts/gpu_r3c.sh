@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 600 python scripts/gram_check.py 1 > gpurun_out/r3c_gram.log 2>&1; cat gpurun_out/r3c_gram.log
+PAREBEN_LIB=pareben_b200/libpareben_timing.so timeout 300 python scripts/phase_timing.py gaussian > gpurun_out/r3c_pt_gauss.log 2>&1; cat gpurun_out/r3c_pt_gauss.log
+PAREBEN_LIB=pareben_b200/libpareben_timing.so timeout 300 python scripts/phase_timing.py binomial > gpurun_out/r3c_pt_binom.log 2>&1; cat gpurun_out/r3c_pt_binom.log
