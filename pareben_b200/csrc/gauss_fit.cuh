@@ -839,23 +839,30 @@ constexpr int SWEEP_PANEL_DOUBLES = 5120;
 
 __device__ inline bool sweep_panel(double *a, int M, double *sm)
 {
+    // While the sweep runs only the LOWER triangle of `a` (element (i, j), i >= j, at a[j*M + i]) is kept current: the
+    // rank-NB update reads and writes each entry once per panel instead of writing it twice (entry and mirror image) --
+    // the matrix lives in L2, and with every block of the grid sweeping, L2 bandwidth is what a panel costs.  The upper
+    // triangle is rebuilt (and the sign flipped) once at the end.  Returns with the NEGATED inverse's sign already
+    // restored, i.e. a = inverse.
     const int T = blockDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
     const int gm = lane >> 2, gk = lane & 3;
     const int Mp = ((M + 7) & ~7) + 4;                    // row stride of the panel arrays (tiles may read up to 7 past M)
     int NB = 8;
-    while (NB > 2 && 3 * NB * Mp + NB > SWEEP_PANEL_DOUBLES) NB >>= 1;
+    while (NB > 2 && 2 * NB * Mp + NB > SWEEP_PANEL_DOUBLES) NB >>= 1;
     const int KS = (NB + 3) >> 2;                         // k-steps of the rank-NB update (NB = 2 is padded to 4 with zero rows)
     const int NBp = 4 * KS;
-    double *Pn = sm, *C = sm + NBp * Mp, *D = C + NBp * Mp, *dv = D + NBp * Mp;
-    const int nt = (M + 7) >> 3, ntile = nt * (nt + 1) / 2;
+    double *Pn = sm, *C = sm + NBp * Mp, *dv = C + NBp * Mp;      // dv[p] = 1 / pivot p (0 for the padding rows)
+    const int nt = (M + 7) >> 3;
     bool ok = true;
     for (int k0 = 0; k0 < M; k0 += NB) {
         const int nb = min(NB, M - k0);
         __syncthreads();
+        // panel columns k0 .. k0+nb-1, all rows: rows above the diagonal come from the mirror-image entries
         for (int idx = threadIdx.x; idx < NBp * Mp; idx += T) {
-            const int q = idx / Mp, i = idx - q * Mp;
-            Pn[idx] = (q < nb && i < M) ? a[(size_t)(k0 + q) * M + i] : 0.0;
-            C[idx] = 0.0; D[idx] = 0.0;                   // rows past nb and entries past M contribute nothing to the update
+            const int q = idx / Mp, i = idx - q * Mp, j = k0 + q;
+            Pn[idx] = (q < nb && i < M) ? (i >= j ? a[(size_t)j * M + i] : a[(size_t)i * M + j]) : 0.0;
+            C[idx] = 0.0;                                 // rows past nb and entries past M contribute nothing to the update
+            if (idx < NBp) dv[idx] = 0.0;
         }
         // phase A: the pivots of this panel, applied to the panel's own columns
         for (int p = 0; p < nb; p++) {
@@ -868,7 +875,6 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
             if (!(d > 0.0)) { ok = false; break; }        // uniform: every thread reads the same value
             const double dinv = 1.0 / d;
             if (threadIdx.x == 0) dv[p] = dinv;
-            for (int i = threadIdx.x; i < M; i += T) D[p * Mp + i] = cp[i] * dinv;
             for (int q = wid; q < nb; q += nw) {              // a warp per panel column, lanes over rows (no integer division)
                 const int j = k0 + q;
                 const double cj = cp[j];
@@ -884,56 +890,71 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
         }
         if (!ok) break;
         __syncthreads();
-        // phase B: rank-nb update of the lower triangle, mirrored.  A warp works on PB tiles at a time: the tile's own
-        // entries come from L2 and a single load -> DMMA -> store chain per warp would pay that latency once per tile.
+        const double dv0 = dv[gk], dv1 = KS > 1 ? dv[4 + gk] : 0.0;     // B fragments are C_p[j] / d_p, formed on the fly
+        // phase B: rank-nb update of the lower triangle.  A warp owns tile rows ti and nt-1-ti (together nt + 1 tiles, so
+        // the warps are balanced) and works on PB tiles at a time: the tile's own entries come from L2 and a single
+        // load -> DMMA -> store chain per warp would pay that latency once per tile.  Tiles that lie inside the panel's own
+        // rows or columns are skipped: phase A has produced those entries and the write-back below stores them.
         constexpr int PB = 4;
-        for (int tb = wid; tb < ntile; tb += nw * PB) {
-            int ti_[PB], tj_[PB];
-            double c0[PB], c1[PB];
-#pragma unroll
-            for (int u = 0; u < PB; u++) {
-                const int t = tb + u * nw;
-                int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-                while (ti * (ti + 1) / 2 > t) ti--;
-                while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-                ti_[u] = ti; tj_[u] = t - ti * (ti + 1) / 2;
-                const bool lv = t < ntile;
-                const int i = 8 * ti + gm, j0 = 8 * tj_[u] + 2 * gk;      // this lane's elements: (i, j0) and (i, j0 + 1)
-                c0[u] = (lv && i < M && j0 < M) ? a[(size_t)j0 * M + i] : 0.0;
-                c1[u] = (lv && i < M && j0 + 1 < M) ? a[(size_t)(j0 + 1) * M + i] : 0.0;
-            }
-#pragma unroll
-            for (int ks = 0; ks < 2; ks++) {
-                if (ks < KS) {
+        const int tp0 = k0 >> 3, tp1 = (k0 + nb + 7) >> 3;             // tile rows / columns [tp0, tp1) belong to the panel (NB = 8: exactly one)
+        const bool panel_aligned = NB == 8;                              // narrower panels share a tile with other columns: update everything
+        for (int pr = wid; 2 * pr < nt; pr += nw) {
+            for (int half = 0; half < 2; half++) {
+                const int ti = half == 0 ? pr : nt - 1 - pr;
+                if (half == 1 && ti == pr) break;                        // middle row of an odd count: once
+                if (panel_aligned && ti >= tp0 && ti < tp1) continue;
+                const double af0 = -C[(gk) * Mp + 8 * ti + gm];
+                const double af1 = KS > 1 ? -C[(4 + gk) * Mp + 8 * ti + gm] : 0.0;
+                const int i = 8 * ti + gm;
+                for (int tb = 0; tb <= ti; tb += PB) {
+                    double c0[PB], c1[PB];
 #pragma unroll
                     for (int u = 0; u < PB; u++) {
-                        if (tb + u * nw < ntile) {                         // warp-uniform
-                            const double af = -C[(4 * ks + gk) * Mp + 8 * ti_[u] + gm];
-                            const double bf = D[(4 * ks + gk) * Mp + 8 * tj_[u] + gm];
-                            dmma(c0[u], c1[u], af, bf);
+                        const int tj = tb + u, j0 = 8 * tj + 2 * gk;     // this lane's elements: (i, j0) and (i, j0 + 1)
+                        const bool lv = tj <= ti;
+                        c0[u] = (lv && i < M && j0 < M) ? a[(size_t)j0 * M + i] : 0.0;
+                        c1[u] = (lv && i < M && j0 + 1 < M) ? a[(size_t)(j0 + 1) * M + i] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < PB; u++) {
+                        const int tj = tb + u;
+                        if (tj <= ti) {                                   // warp-uniform
+                            dmma(c0[u], c1[u], af0, C[(gk) * Mp + 8 * tj + gm] * dv0);
+                            if (KS > 1) dmma(c0[u], c1[u], af1, C[(4 + gk) * Mp + 8 * tj + gm] * dv1);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PB; u++) {
+                        const int tj = tb + u, j0 = 8 * tj + 2 * gk;
+                        if (tj <= ti && !(panel_aligned && tj >= tp0 && tj < tp1)) {
+                            if (i < M && j0 < M && i >= j0) a[(size_t)j0 * M + i] = c0[u];
+                            if (i < M && j0 + 1 < M && i >= j0 + 1) a[(size_t)(j0 + 1) * M + i] = c1[u];
                         }
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < PB; u++) {
-                if (tb + u * nw < ntile) {
-                    const int i = 8 * ti_[u] + gm, j0 = 8 * tj_[u] + 2 * gk;
-                    const bool diag = ti_[u] == tj_[u];
-                    if (i < M && j0 < M && (!diag || i >= j0)) { a[(size_t)j0 * M + i] = c0[u]; a[(size_t)i * M + j0] = c0[u]; }
-                    if (i < M && j0 + 1 < M && (!diag || i >= j0 + 1)) { a[(size_t)(j0 + 1) * M + i] = c1[u]; a[(size_t)i * M + j0 + 1] = c1[u]; }
-                }
-            }
         }
         __syncthreads();
-        // the panel's own columns, and their mirror image: the rows of the panel's pivots
-        for (int idx = threadIdx.x; idx < nb * M; idx += T) {
-            const int q = idx / M, i = idx - q * M;
-            const double v = Pn[q * Mp + i];
-            a[(size_t)(k0 + q) * M + i] = v;
-            a[(size_t)i * M + k0 + q] = v;
+        // the panel's own columns: below the diagonal in place, above it at the mirror-image position (row k0+q of the
+        // lower triangle)
+        for (int q = 0; q < nb; q++) {
+            const int j = k0 + q;
+            for (int i = threadIdx.x; i < M; i += T) {
+                const double v = Pn[q * Mp + i];
+                if (i >= j) a[(size_t)j * M + i] = v;
+                else if (i < k0) a[(size_t)i * M + j] = v;        // (k0 <= i < j: that entry is column i's, written by its own pass)
+            }
         }
     }
+    __syncthreads();
+    // sign, and the upper triangle from the lower one: warps own columns j, lanes rows i >= j
+    if (ok)
+        for (int j = wid; j < M; j += nw)
+            for (int i = j + lane; i < M; i += 32) {
+                const double v = -a[(size_t)j * M + i];
+                a[(size_t)j * M + i] = v;
+                if (i != j) a[(size_t)i * M + j] = v;
+            }
     __syncthreads();
     return ok;
 }
@@ -1009,11 +1030,14 @@ __device__ inline bool spd_inverse_sweep(double *a, int M, double *colk, const S
     if (sm && M <= SWEEP_SMEM_M && T == 256) {
         ok = M <= 32 ? sweep_regs<1>(a, M, sm) : sweep_regs<2>(a, M, sm);
     } else {
-        // the panel arrays need 3 * 4 * (M rounded up to 8, + 4) doubles even at the narrowest panel: beyond that
-        // (M > 420) the one-pivot sweep in global memory takes over
-        const bool panel_fits = 12 * (((M + 7) & ~7) + 4) + 8 <= SWEEP_PANEL_DOUBLES;
-        ok = (sm && panel_fits) ? sweep_panel(a, M, sm) : sweep_core(a, M, colk);          // colk: 2*(cap+1) doubles in the slab
-        if (ok) for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -a[idx];
+        // the panel arrays need 2 * 4 * (M rounded up to 8, + 4) doubles even at the narrowest panel: beyond that
+        // (M > 632) the one-pivot sweep in global memory takes over
+        const bool panel_fits = 8 * (((M + 7) & ~7) + 4) + 8 <= SWEEP_PANEL_DOUBLES;
+        if (sm && panel_fits) ok = sweep_panel(a, M, sm);                                  // (restores the sign itself)
+        else {
+            ok = sweep_core(a, M, colk);                                                   // colk: 2*(cap+1) doubles in the slab
+            if (ok) for (int idx = threadIdx.x; idx < M * M; idx += T) a[idx] = -a[idx];
+        }
     }
     __syncthreads();
     return ok;
