@@ -891,46 +891,45 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
         if (!ok) break;
         __syncthreads();
         const double dv0 = dv[gk], dv1 = KS > 1 ? dv[4 + gk] : 0.0;     // B fragments are C_p[j] / d_p, formed on the fly
-        // phase B: rank-nb update of the lower triangle.  A warp owns tile rows ti and nt-1-ti (together nt + 1 tiles, so
-        // the warps are balanced) and works on PB tiles at a time: the tile's own entries come from L2 and a single
-        // load -> DMMA -> store chain per warp would pay that latency once per tile.  Tiles that lie inside the panel's own
-        // rows or columns are skipped: phase A has produced those entries and the write-back below stores them.
-        constexpr int PB = 4;
-        const int tp0 = k0 >> 3, tp1 = (k0 + nb + 7) >> 3;             // tile rows / columns [tp0, tp1) belong to the panel (NB = 8: exactly one)
+        // phase B: rank-nb update of the lower triangle.  The nt (nt + 1) / 2 tiles, row-major, are cut into one contiguous
+        // range per warp (balanced to a tile); a warp works on PB tiles at a time: the tile's own entries come from L2 and a
+        // single load -> DMMA -> store chain per warp would pay that latency once per tile.  Tiles that lie inside the
+        // panel's own rows or columns are skipped: phase A has produced those entries and the write-back below stores them.
+        constexpr int PB = 8;
+        const int tp0 = k0 >> 3;                                         // NB = 8: tile row / column tp0 is the panel's
         const bool panel_aligned = NB == 8;                              // narrower panels share a tile with other columns: update everything
-        for (int pr = wid; 2 * pr < nt; pr += nw) {
-            for (int half = 0; half < 2; half++) {
-                const int ti = half == 0 ? pr : nt - 1 - pr;
-                if (half == 1 && ti == pr) break;                        // middle row of an odd count: once
-                if (panel_aligned && ti >= tp0 && ti < tp1) continue;
-                const double af0 = -C[(gk) * Mp + 8 * ti + gm];
-                const double af1 = KS > 1 ? -C[(4 + gk) * Mp + 8 * ti + gm] : 0.0;
-                const int i = 8 * ti + gm;
-                for (int tb = 0; tb <= ti; tb += PB) {
-                    double c0[PB], c1[PB];
+        const int ntile = nt * (nt + 1) / 2;
+        const int t_begin = (int)((long long)ntile * wid / nw), t_end = (int)((long long)ntile * (wid + 1) / nw);
+        int ti = (int)((sqrt(8.0 * t_begin + 1.0) - 1.0) * 0.5);
+        while (ti * (ti + 1) / 2 > t_begin) ti--;
+        while ((ti + 1) * (ti + 2) / 2 <= t_begin) ti++;
+        int tj = t_begin - ti * (ti + 1) / 2;
+        for (int tb = t_begin; tb < t_end; tb += PB) {
+            int ti_[PB], tj_[PB];
+            double c0[PB], c1[PB];
 #pragma unroll
-                    for (int u = 0; u < PB; u++) {
-                        const int tj = tb + u, j0 = 8 * tj + 2 * gk;     // this lane's elements: (i, j0) and (i, j0 + 1)
-                        const bool lv = tj <= ti;
-                        c0[u] = (lv && i < M && j0 < M) ? a[(size_t)j0 * M + i] : 0.0;
-                        c1[u] = (lv && i < M && j0 + 1 < M) ? a[(size_t)(j0 + 1) * M + i] : 0.0;
-                    }
+            for (int u = 0; u < PB; u++) {
+                ti_[u] = ti; tj_[u] = tj;
+                const bool lv = tb + u < t_end && !(panel_aligned && (ti == tp0 || tj == tp0));
+                if (!lv) ti_[u] = -1;
+                const int i = 8 * ti + gm, j0 = 8 * tj + 2 * gk;          // this lane's elements: (i, j0) and (i, j0 + 1)
+                c0[u] = (lv && i < M && j0 < M) ? a[(size_t)j0 * M + i] : 0.0;
+                c1[u] = (lv && i < M && j0 + 1 < M) ? a[(size_t)(j0 + 1) * M + i] : 0.0;
+                if (++tj > ti) { ti++; tj = 0; }
+            }
 #pragma unroll
-                    for (int u = 0; u < PB; u++) {
-                        const int tj = tb + u;
-                        if (tj <= ti) {                                   // warp-uniform
-                            dmma(c0[u], c1[u], af0, C[(gk) * Mp + 8 * tj + gm] * dv0);
-                            if (KS > 1) dmma(c0[u], c1[u], af1, C[(4 + gk) * Mp + 8 * tj + gm] * dv1);
-                        }
-                    }
+            for (int u = 0; u < PB; u++) {
+                if (ti_[u] >= 0) {                                        // warp-uniform
+                    dmma(c0[u], c1[u], -C[(gk) * Mp + 8 * ti_[u] + gm], C[(gk) * Mp + 8 * tj_[u] + gm] * dv0);
+                    if (KS > 1) dmma(c0[u], c1[u], -C[(4 + gk) * Mp + 8 * ti_[u] + gm], C[(4 + gk) * Mp + 8 * tj_[u] + gm] * dv1);
+                }
+            }
 #pragma unroll
-                    for (int u = 0; u < PB; u++) {
-                        const int tj = tb + u, j0 = 8 * tj + 2 * gk;
-                        if (tj <= ti && !(panel_aligned && tj >= tp0 && tj < tp1)) {
-                            if (i < M && j0 < M && i >= j0) a[(size_t)j0 * M + i] = c0[u];
-                            if (i < M && j0 + 1 < M && i >= j0 + 1) a[(size_t)(j0 + 1) * M + i] = c1[u];
-                        }
-                    }
+            for (int u = 0; u < PB; u++) {
+                if (ti_[u] >= 0) {
+                    const int i = 8 * ti_[u] + gm, j0 = 8 * tj_[u] + 2 * gk;
+                    if (i < M && j0 < M && i >= j0) a[(size_t)j0 * M + i] = c0[u];
+                    if (i < M && j0 + 1 < M && i >= j0 + 1) a[(size_t)(j0 + 1) * M + i] = c1[u];
                 }
             }
         }
@@ -1447,6 +1446,10 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
         vk0 = vk;
         for (int h = threadIdx.x; h < N; h += T) s.t[h] = y[h] - b;
         __syncthreads();
+        const double vt = block_var(s.t, N, sc);                    // t is fixed for the whole inner solver (:705 recomputes it per noise update)
+        double tt = 0;
+        for (int h = threadIdx.x; h < N; h += T) tt = fma(s.t[h], s.t[h], tt);
+        tt = block_sum(tt, sc);
         // ---------------- inner solver (LinearFastEmpBayes*, MainEff.c:248-809) ----------------
         int ini_removed = 1;
         if (iter <= 1) {                                             // initialisation, :1003-1090
@@ -1594,9 +1597,10 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             }
                             if (threadIdx.x == 0) s.ptp[(size_t)M * cap + M] = s.G[(size_t)grow_new * Kc + nu];
                             __syncthreads();
-                            for (int i = threadIdx.x; i < M; i += T) {
+                            for (int i = threadIdx.x; i < M; i += T) {       // SIGMA is symmetric: walk column i so that a warp's loads coalesce
                                 double z = 0;
-                                for (int j = 0; j < M; j++) z = fma(s.sigma[i * M + j], s.tmp[j], z);
+#pragma unroll 4
+                                for (int j = 0; j < M; j++) z = fma(s.sigma[j * M + i], s.tmp[j], z);
                                 s.u[i] = z;
                             }
                             for (int h = threadIdx.x; h < LD; h += T) s.phi[(size_t)M * LD + h] = h < N ? s.phinew[h] : 0.0;
@@ -1720,24 +1724,23 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                 const int M = g.M;
                 double ee = 0;
                 { PHASE(PH_LOGLIK);
-                for (int h = threadIdx.x; h < N; h += 2 * T) {          // two rows per thread: twice the loads in flight
-                    const int h2 = h + T;
-                    const bool two = h2 < N;
-                    const double *pa = s.phi + h, *pb = s.phi + (two ? h2 : h);
-                    double pm = 0, pm2 = 0;
-#pragma unroll 4
-                    for (int j = 0; j < M; j++) { const double m = s.mu[j]; pm = fma(pa[(size_t)j * LD], m, pm); pm2 = fma(pb[(size_t)j * LD], m, pm2); }
-                    const double e = s.t[h] - pm;
-                    ee = fma(e, e, ee);
-                    if (two) { const double e2 = s.t[h2] - pm2; ee = fma(e2, e2, ee); }
+                // ||t - PHI mu||^2 = t't - 2 mu'(PHI't) + mu'(PHI'PHI)mu: PHI't is xt at the active candidates and PHI'PHI is
+                // kept by the actions, so the residual costs M^2 instead of a pass over the N x M matrix PHI (the
+                // cancellation costs a factor t't / ee <= 100 in relative accuracy -- the outer loop stops at 1 % -- of 1e-16)
+                double part = 0;
+                for (int j = wid_; j < M; j += nw_) {
+                    const double *pr = s.ptp + (size_t)j * cap;
+                    double z = 0;
+                    for (int i = lane_; i < M; i += 32) z = fma(pr[i], s.mu[i], z);
+                    z = warp_sum(z);
+                    if (lane_ == 0) part += s.mu[j] * (z - 2 * s.xt[s.used[j] - 1]);
                 }
-                ee = block_sum(ee, sc);
+                ee = tt + block_sum(part, sc);
                 }
                 double sg = 0;
                 for (int i = 0; i < M; i++) sg += s.gamma[i];
                 const double beta_old = g.beta;
                 g.beta = (N - sg) / ee;
-                const double vt = block_var(s.t, N, sc);
                 if (g.beta > 1e6 / vt) g.beta = 1e6 / vt;
                 if (fabs(log(g.beta) - log(beta_old)) > 1e-6) {
                     if (!final_update(s, g, N, sc)) g.status |= ST_NOT_PD;
@@ -1763,7 +1766,8 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
             double q11 = 0, q1y = 0, sy = 0;
             for (int j = threadIdx.x; j < M; j += T) {
                 double z = 0;
-                for (int k = 0; k < M; k++) z = fma(s.sigma[j * M + k], s.tmp[k], z);
+#pragma unroll 4
+                for (int k = 0; k < M; k++) z = fma(s.sigma[k * M + j], s.tmp[k], z);      // (symmetric: coalesced column walk)
                 q11 = fma(z, s.tmp[j], q11); q1y = fma(z, s.u[j], q1y);
             }
             block_sum2(q11, q1y, sc);
