@@ -149,6 +149,14 @@ int pareben_sl_filter(pareben_problem *p, double tau_main, double tau_pair, int 
  * (SURVEY.md 8d): algorithmic FP64 flops of the contraction/statistics phases, kernel
  * milliseconds measured with CUDA events on the launch stream, launches issued. */
 int pareben_last_counters(pareben_problem *p, double *flops, double *kernel_ms, int *launches);
+/* Gram organisation of the Gaussian cached kernels.  The candidate-cache row of a basis (CacheBP*,
+ * /root/reference/EBEN_orig/src/elasticNetLinearNeMainEff.c:1144-1201; ActionAdd* :1608-1618) depends on the fold only, so
+ * the library builds it once per fold for every candidate (8 Kc^2 bytes per fold, when that fits in half of the free
+ * device memory and the call has enough fits to amortise 2 N Kc^2 flops per fold; PAREBEN_GRAM=0 / 1 overrides the work
+ * test) and all fits of the fold share it.  in_use: 1 when the problem runs that way; avoided_flops: the part of
+ * pareben_last_counters' model flops that the last call did not have to execute; build_ms: time the last call spent
+ * building the matrices (0 once they exist; it is included in that call's kernel_ms). */
+int pareben_last_gram_info(pareben_problem *p, int *in_use, double *avoided_flops, double *build_ms);
 
 /* Solver organisation.  mode 0 (default) = automatic, 1 = cached kernel, 2 = streaming kernels.
  * The cached kernel keeps the reference's per-fit candidate cache (BASIS_PHI, one row of Kc doubles per active basis,

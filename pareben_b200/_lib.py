@@ -41,6 +41,7 @@ SIGNATURES = {
     "pareben_lambda_max": (ctypes.c_int, [_vp, _dp]),
     "pareben_sl_filter": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, _ip, _dp, _ip]),
     "pareben_last_counters": (ctypes.c_int, [_vp, _dp, _dp, _ip]),
+    "pareben_last_gram_info": (ctypes.c_int, [_vp, _ip, _dp, _dp]),
     "pareben_set_mode": (ctypes.c_int, [ctypes.c_int]),
     "pareben_is_streaming": (ctypes.c_int, [_vp]),
     "pareben_last_stream_counters": (ctypes.c_int, [_vp, _dp, _dp, _ip, _ip]),
@@ -207,6 +208,13 @@ class Problem:
         fl = np.zeros(1); ms = np.zeros(1); ln = np.zeros(1, np.int32)
         _check(load().pareben_last_counters(self._h, _d(fl), _d(ms), _i(ln)))
         return float(fl[0]), float(ms[0]), int(ln[0])
+
+    def gram_info(self):
+        """(in use, model flops the last run_fits did not execute, ms the last run_fits spent building the matrices):
+        the Gram organisation of the Gaussian cached kernels (include/pareben.h, pareben_last_gram_info)."""
+        use = np.zeros(1, np.int32); av = np.zeros(1); ms = np.zeros(1)
+        _check(load().pareben_last_gram_info(self._h, _i(use), _d(av), _d(ms)))
+        return bool(use[0]), float(av[0]), float(ms[0])
 
 
 def cv_grid(BASIS, Target, fold_id, n_folds, alpha, lam, epis=False, prior="gaussian", device=None,

@@ -21,6 +21,7 @@ struct GaussState {
     double beta;
     int status;
     double flops;
+    double avoided;          // the part of `flops` (SURVEY 8d model) that the Gram organisation did not execute
 };
 
 // ---- contraction: out(r, c) = sum_h x_c[h] * V_r[h]  for r in [0,R), c in [0,Kc) -------------
@@ -1425,7 +1426,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
     const int N = F.ntr, K = P.K, Kc = P.Kc, cap = P.cap, T = blockDim.x, LD = phi_ld(N);
     const int lane_ = threadIdx.x & 31, wid_ = threadIdx.x >> 5, nw_ = T >> 5;
     const double *X = F.Xtr, *y = F.ytr, *scale = F.scale;
-    GaussState g; g.M = 1; g.n_unused = 0; g.cap = cap; g.beta = 0; g.status = 0; g.flops = 0;
+    GaussState g; g.M = 1; g.n_unused = 0; g.cap = cap; g.beta = 0; g.status = 0; g.flops = 0; g.avoided = 0;
     // Gram organisation: the cache row of basis p is row p of the fold's shared matrix C (FoldData::C), so the cache is
     // never computed or stored per fit -- `grow[j]` simply holds the candidate id of active slot j, and every reader of
     // the cache (quadratic forms, S/Q corrections) streams rows that all fits of the fold share in L2.
@@ -1492,7 +1493,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                     [&](int r) -> const double * { return r < M ? s.phi + (size_t)r * LD : s.t; },
                     [&](int r, bool &dv) -> double * { dv = true; return r < M ? s.G + (size_t)s.grow[r] * Kc : s.xt; },
                     sV);
-            if (threadIdx.x == 0) g.flops += 2.0 * N * (double)Kc * (M + 1);     // the SURVEY 8d model of this step (gram: only 2 N Kc executed)
+            if (threadIdx.x == 0) { g.flops += 2.0 * N * (double)Kc * (M + 1); if (gram) g.avoided += 2.0 * N * (double)Kc * M; }     // the SURVEY 8d model of this step
         }
         int i_iter = 0;
         full_stat(s, g, N, Kc, iter == 1, sc);
@@ -1639,6 +1640,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                                 const int p = s.upos[nu], nun = g.n_unused - 1;   // Unused: swap-with-last (:621-625)
                                 if (p < nun) { const int lastc = s.unused[nun] - 1; s.unused[p] = lastc + 1; s.upos[lastc] = p; }
                                 g.flops += 2.0 * N * (double)Kc + 2.0 * Kc * (double)M;
+                                if (gram) g.avoided += 2.0 * N * (double)Kc;
                             }
                             g.n_unused--;
                             g.M = M + 1;
@@ -1810,7 +1812,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
         if (out.status) out.status[o] = g.status;
         if (out.n_selected) out.n_selected[o] = nsel;
         if (out.n_iter) out.n_iter[o] = iter;
-        if (out.flops) atomicAdd(out.flops, g.flops);
+        if (out.flops) { atomicAdd(out.flops, g.flops); if (g.avoided > 0) atomicAdd(out.flops + 1, g.avoided); }
         if (out.m_out) {          // full-model dump (pareben_fit)
             out.m_out[0] = M;
             double wd = 0;        // Wald score mu'H mu with H read at leading dimension M (:206-215)

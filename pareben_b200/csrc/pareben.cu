@@ -153,6 +153,29 @@ __global__ void gather_vec_kernel(const double *__restrict__ y, const int *__res
     if (r < nrows) out[r] = y[rows[r]];
 }
 
+// The transposed int8 training matrix (and its element-wise squares; the caller has checked |x| <= 11) in the
+// fragment-major order of imma_contract.cuh: 16-byte piece ((mt * KP + kp) * 32 + lane) * 2 + half holds positions
+// 64 kp + 16 (lane % 4) .. + 15 of candidate 16 mt + 8 half + lane / 4 (zeros past the last candidate).
+__global__ void fragment_major_kernel(const int8_t *__restrict__ XT8, int K, int ldt, int8_t *__restrict__ out, int8_t *__restrict__ out_sq)
+{
+    const int KP = ldt >> 6;
+    const size_t n_piece = (size_t)((K + 15) >> 4) * KP * 64;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_piece; i += (size_t)gridDim.x * blockDim.x) {
+        const int half = (int)(i & 1), lane = (int)((i >> 1) & 31);
+        const size_t t = i >> 6;
+        const int kp = (int)(t % KP), mt = (int)(t / KP);
+        const int c = mt * 16 + half * 8 + (lane >> 2);
+        int4 v = make_int4(0, 0, 0, 0), q = v;
+        if (c < K) {
+            v = *reinterpret_cast<const int4 *>(XT8 + (size_t)c * ldt + kp * 64 + (lane & 3) * 16);
+            auto sq = [](int w) { int o = 0; for (int b = 0; b < 4; b++) { const int x = (int)(int8_t)((unsigned)w >> (8 * b)); o |= ((x * x) & 0xff) << (8 * b); } return o; };
+            q = make_int4(sq(v.x), sq(v.y), sq(v.z), sq(v.w));
+        }
+        reinterpret_cast<int4 *>(out)[i] = v;
+        reinterpret_cast<int4 *>(out_sq)[i] = q;
+    }
+}
+
 __global__ void to_int8_kernel(const double *__restrict__ in, size_t n, int8_t *__restrict__ out)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -294,6 +317,7 @@ struct pareben_problem {
     // Gram organisation (Gaussian, cached kernels): FoldData::C per fold, built on first use and kept with the problem
     int gram_state = 0;                  // 0 = undecided, 1 = in use, -1 = refused (memory or too little work)
     double gram_ms = 0; int gram_launches = 0;      // time / launches spent building C in the last run_fits call
+    double last_avoided = 0;             // model flops of the last call that the Gram organisation did not execute
     double last_scan_ms = 0, last_scan_flops = 0; int last_scan_launches = 0, last_rounds = 0;
 
     template <class T> T *dalloc(size_t n)
@@ -338,7 +362,11 @@ static void ensure_slabs(pareben_problem *p)
     if (p->cap < 2) p->cap = 2;
 
     // persistent grid: blocks per SM limited by memory for slabs
-    p->slab_stride = slab_bytes(p->cap, p->nmax, p->kc);
+    #ifdef PAREBEN_IMMA
+    p->slab_stride = slab_bytes(p->cap, p->nmax, p->kc, p->prior == PAREBEN_BINOMIAL ? 1 : 0);
+#else
+    p->slab_stride = slab_bytes(p->cap, p->nmax, p->kc, 0);
+#endif
     // resident blocks per SM of the kernel variant this problem will launch (asked once per variant:
     // the occupancy query, like cudaMemGetInfo below, costs up to tens of milliseconds)
     int per_sm = 1;
@@ -496,10 +524,17 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         // int8 copy of the training matrices: the score contraction reads 1 byte instead of 8 per
         // element and widens in registers (exact).
         bool small_int = getenv("PAREBEN_NO_INT8") == nullptr;
+        [[maybe_unused]] bool tiny_int = true;            // |x| <= 11: the squares fit in int8 too (binomial int8 contraction, experiment)
         for (size_t i = 0, e = (size_t)n * k; small_int && i < e; i++) {
             const double v = basis[i];
             if (!(v >= -127.0 && v <= 127.0) || v != (double)(int)v) small_int = false;
+            if (!(v >= -11.0 && v <= 11.0)) tiny_int = false;
         }
+#ifdef PAREBEN_IMMA
+        const bool want_sq = small_int && tiny_int && prior == PAREBEN_BINOMIAL && !epis && getenv("PAREBEN_NO_IMMA") == nullptr;
+#else
+        const bool want_sq = false; (void)tiny_int;       // the int8 tensor-core contraction is an experiment (imma_contract.cuh), not built by default
+#endif
         lap("stream/events/h2d enqueue/scan");
         // row lists per fold: index 0 = all rows (only materialised when n_folds == 0)
         const int nf = n_folds;
@@ -539,7 +574,7 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
                 else scales_kernel<false><<<(p->kc + 255) / 256, 256, 0, p->stream>>>(Xtr, F.ntr, k, p->kc, scale);
             }
             F.Xtr = Xtr; F.ytr = ytr; F.Xte = Xte; F.yte = yte; F.scale = scale; F.Xtr8 = nullptr;
-            F.XT8 = nullptr; F.XTd = nullptr;
+            F.XT8 = nullptr; F.XTd = nullptr; F.XT8f = nullptr; F.XT8sqf = nullptr; F.C = nullptr;
             F.ldt = (F.ntr + 63) & ~63;      // whole stages of the contraction (KT = 64 rows)
             {
                 const dim3 tg((F.ldt + 31) / 32, (k + 31) / 32);
@@ -547,6 +582,12 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
                     int8_t *t8 = p->dalloc<int8_t>((size_t)F.ldt * k + 16);
                     transpose_pad_kernel<int8_t><<<tg, blk, 0, p->stream>>>(Xtr, F.ntr, k, F.ldt, t8);
                     F.XT8 = t8;
+                    if (want_sq) {
+                        const size_t fb = (size_t)((k + 15) / 16) * 16 * F.ldt;
+                        int8_t *t8f = p->dalloc<int8_t>(fb), *t8sqf = p->dalloc<int8_t>(fb);
+                        fragment_major_kernel<<<(int)std::min<size_t>(1024, (fb / 16 + 255) / 256), 256, 0, p->stream>>>(t8, k, F.ldt, t8f, t8sqf);
+                        F.XT8f = t8f; F.XT8sqf = t8sqf;
+                    }
                 } else {
                     double *td = p->dalloc<double>((size_t)F.ldt * k + 4);
                     transpose_pad_kernel<double><<<tg, blk, 0, p->stream>>>(Xtr, F.ntr, k, F.ldt, td);
@@ -565,7 +606,7 @@ extern "C" int pareben_problem_create(pareben_problem **out, int device, const d
         CU(cudaMemcpyAsync(p->d_folds, p->h_folds.data(), sizeof(FoldData) * (nf + 1), cudaMemcpyHostToDevice, p->stream));
 
         p->min_ntr = min_ntr;
-        p->d_flops = p->dalloc<double>(1);
+        p->d_flops = p->dalloc<double>(2);
         CU(cudaStreamSynchronize(p->stream));
         lap("final sync");
     } catch (std::pair<int, std::string> &e) {
@@ -678,7 +719,7 @@ int run_fits_streaming(pareben_problem *p, int n_fits, const int *fold, const do
         double *d_wscratch = (double *)tmp_alloc(sizeof(double) * (size_t)scan_grid * SCAN_WARPS * cap);
         double *d_err = (double *)tmp_alloc(sizeof(double) * n_fits);
         int *d_ints = (int *)tmp_alloc(sizeof(int) * 3 * n_fits);
-        CU(cudaMemsetAsync(p->d_flops, 0, sizeof(double), p->stream));
+        CU(cudaMemsetAsync(p->d_flops, 0, 2 * sizeof(double), p->stream));
         CU(cudaMemsetAsync(d_nslots, 0, sizeof(int) * nvf, p->stream));
         StreamShared sh;
         sh.folds = d_sf; sh.n_slots = d_nslots; sh.list_cap = list_cap; { const char *w = getenv("PAREBEN_STREAM_WIDE"); sh.wide = w ? atoi(w) : 0; } sh.warp_scratch = d_wscratch; sh.flops = p->d_flops;
@@ -815,7 +856,7 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
         sched.t_start = d_sched; sched.cost = d_sched + n_groups; sched.taken = reinterpret_cast<int *>(d_sched + 2 * (size_t)n_groups);
         CU(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(FitTask) * n_fits, cudaMemcpyHostToDevice, p->stream));
         CU(cudaMemsetAsync(d_sched, 0, sched_bytes, p->stream));
-        CU(cudaMemsetAsync(p->d_flops, 0, sizeof(double), p->stream));
+        CU(cudaMemsetAsync(p->d_flops, 0, 2 * sizeof(double), p->stream));
         FitOutputs out;
         out.fold_err = d_err; out.status = d_ints; out.n_selected = d_ints + n_fits; out.n_iter = d_ints + 2 * n_fits;
         out.m_out = nullptr; out.used_out = nullptr; out.beta_out = nullptr; out.var_out = nullptr; out.scalars_out = nullptr;
@@ -842,9 +883,11 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
         std::vector<double> h_err(n_fits);
         CU(cudaMemcpyAsync(h_err.data(), d_err, sizeof(double) * n_fits, cudaMemcpyDeviceToHost, p->stream));
         CU(cudaMemcpyAsync(h_ints.data(), d_ints, sizeof(int) * 3 * n_fits, cudaMemcpyDeviceToHost, p->stream));
-        double h_flops = 0;
-        CU(cudaMemcpyAsync(&h_flops, p->d_flops, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        double h_flops2[2] = {0, 0};
+        CU(cudaMemcpyAsync(h_flops2, p->d_flops, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
+        const double h_flops = h_flops2[0];
+        p->last_avoided = h_flops2[1];
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
         p->last_ms = ms + p->gram_ms; p->last_flops = h_flops; p->last_launches = 1 + p->gram_launches;      // a call that had to build C pays for it
@@ -1250,6 +1293,15 @@ extern "C" int pareben_last_stream_counters(pareben_problem *p, double *scan_ms,
     if (scan_flops) *scan_flops = p->last_scan_flops;
     if (scan_launches) *scan_launches = p->last_scan_launches;
     if (rounds) *rounds = p->last_rounds;
+    return PAREBEN_OK;
+}
+
+extern "C" int pareben_last_gram_info(pareben_problem *p, int *in_use, double *avoided_flops, double *build_ms)
+{
+    if (!p) return fail(PAREBEN_EINVAL, "null problem");
+    if (in_use) *in_use = p->gram_state == 1 ? 1 : 0;
+    if (avoided_flops) *avoided_flops = p->last_avoided;
+    if (build_ms) *build_ms = p->gram_ms;
     return PAREBEN_OK;
 }
 
