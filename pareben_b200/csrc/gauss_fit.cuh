@@ -859,12 +859,17 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
         const int nb = min(NB, M - k0);
         __syncthreads();
         // panel columns k0 .. k0+nb-1, all rows: rows above the diagonal come from the mirror-image entries
-        for (int idx = threadIdx.x; idx < NBp * Mp; idx += T) {
-            const int q = idx / Mp, i = idx - q * Mp, j = k0 + q;
-            Pn[idx] = (q < nb && i < M) ? (i >= j ? a[(size_t)j * M + i] : a[(size_t)i * M + j]) : 0.0;
-            C[idx] = 0.0;                                 // rows past nb and entries past M contribute nothing to the update
-            if (idx < NBp) dv[idx] = 0.0;
+        for (int i = threadIdx.x; i < Mp; i += T) {       // a thread takes row i of all panel columns: NBp independent loads, no division
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (q < NBp) {
+                    const int j = k0 + q;
+                    Pn[q * Mp + i] = (q < nb && i < M) ? (i >= j ? a[(size_t)j * M + i] : a[(size_t)i * M + j]) : 0.0;
+                    C[q * Mp + i] = 0.0;                  // rows past nb and entries past M contribute nothing to the update
+                }
+            }
         }
+        if (threadIdx.x < NBp) dv[threadIdx.x] = 0.0;
         // phase A: the pivots of this panel, applied to the panel's own columns
         for (int p = 0; p < nb; p++) {
             __syncthreads();

@@ -318,6 +318,8 @@ struct pareben_problem {
     int gram_state = 0;                  // 0 = undecided, 1 = in use, -1 = refused (memory or too little work)
     double gram_ms = 0; int gram_launches = 0;      // time / launches spent building C in the last run_fits call
     double last_avoided = 0;             // model flops of the last call that the Gram organisation did not execute
+    long long grid_fits_hint = 0;        // fits of the WHOLE grid a sharded call belongs to (0 = unknown): the work test must not
+                                         // depend on how many ways the grid is split, or 1- and 8-GPU tables could differ in rounding
     double last_scan_ms = 0, last_scan_flops = 0; int last_scan_launches = 0, last_rounds = 0;
 
     template <class T> T *dalloc(size_t n)
@@ -445,7 +447,8 @@ static void ensure_gram(pareben_problem *p, int n_fits, const int *fold)
     if (p->gram_state == 0) {
         int n_distinct = 0;
         { std::vector<char> seen(p->h_folds.size(), 0); for (int i = 0; i < n_fits; i++) if (!seen[fold[i]]) { seen[fold[i]] = 1; n_distinct++; } }
-        if (forced != 1 && (double)n_distinct * p->kc > 512.0 * n_fits) return;      // too little work in this call: decide again next time
+        const double work_fits = (double)std::max<long long>(n_fits, p->grid_fits_hint);
+        if (forced != 1 && (double)n_distinct * p->kc > 512.0 * work_fits) return;   // too little work in this call: decide again next time
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         free_b += pool_parked(p->device);
@@ -964,6 +967,7 @@ int cv_grid_on_device(const double *basis, int n, int k, const double *target, c
         const int fit = mine[i];
         fold[i] = fit % n_folds + 1; a[i] = alpha[fit / n_folds]; l[i] = lambda[fit / n_folds];
     }
+    p->grid_fits_hint = total;
     rc = pareben_run_fits(p, m, fold.data(), a.data(), l.data(), err.data(), st.data(), ns.data(), nullptr);
     auto t2 = std::chrono::steady_clock::now();
     const double kernel_ms = p->last_ms;
@@ -1083,7 +1087,9 @@ extern "C" int pareben_problem_cv_grid(pareben_problem *p, const double *alpha, 
     std::vector<int> fold(m), st(m), ns(m);
     std::vector<double> a(m), l(m), err(m);
     for (int i = 0; i < m; i++) { fold[i] = mine[i] % nf + 1; a[i] = alpha[mine[i] / nf]; l[i] = lambda[mine[i] / nf]; }
+    p->grid_fits_hint = total;
     rc = pareben_run_fits(p, m, fold.data(), a.data(), l.data(), err.data(), st.data(), ns.data(), nullptr);
+    p->grid_fits_hint = 0;
     if (rc != PAREBEN_OK) return rc;
     for (int i = 0; i < m; i++) {
         fold_err[mine[i]] = err[i];
