@@ -1283,6 +1283,24 @@ __device__ inline double block_var(const double *t, int N, const Scratch &sc)
     return block_sum(v, sc) / (N - 1);
 }
 
+// (A v)[i] for a symmetric M x M matrix stored with leading dimension M: the thread walks COLUMN i (a warp's loads coalesce)
+// in four interleaved chains, so that sixteen loads of the L2-resident matrix are in flight instead of four behind one
+// dependent FMA chain; the chains are combined in a fixed order.
+__device__ inline double sym_matvec_row(const double *__restrict__ A, int M, int i, const double *__restrict__ v)
+{
+    double z0 = 0, z1 = 0, z2 = 0, z3 = 0;
+    int j = 0;
+#pragma unroll 4
+    for (; j + 4 <= M; j += 4) {
+        z0 = fma(A[(size_t)j * M + i], v[j], z0);
+        z1 = fma(A[(size_t)(j + 1) * M + i], v[j + 1], z1);
+        z2 = fma(A[(size_t)(j + 2) * M + i], v[j + 2], z2);
+        z3 = fma(A[(size_t)(j + 3) * M + i], v[j + 3], z3);
+    }
+    for (; j < M; j++) z0 = fma(A[(size_t)j * M + i], v[j], z0);
+    return (z0 + z1) + (z2 + z3);
+}
+
 __device__ inline void posterior_mean(Slab &s, GaussState &g, int N)
 {   // Mu = beta * SIGMA * PHI' t   (MainEff.c:1256-1280)
     // PHI' t needs no pass over PHI: column j of PHI is candidate used[j]'s normalised column, and x_c' t / s_c is
@@ -1291,11 +1309,7 @@ __device__ inline void posterior_mean(Slab &s, GaussState &g, int N)
     (void)N;
     for (int j = threadIdx.x; j < M; j += blockDim.x) s.tmp[j] = s.xt[s.used[j] - 1];
     __syncthreads();
-    for (int i = threadIdx.x; i < M; i += blockDim.x) {
-        double z = 0;
-        for (int j = 0; j < M; j++) z = fma(s.sigma[j * M + i], s.tmp[j], z);
-        s.mu[i] = z * g.beta;
-    }
+    for (int i = threadIdx.x; i < M; i += blockDim.x) s.mu[i] = sym_matvec_row(s.sigma, M, i, s.tmp) * g.beta;
     __syncthreads();
 }
 
@@ -1321,7 +1335,7 @@ __device__ inline void full_stat(Slab &s, GaussState &g, int N, int Kc, bool fir
     refresh_out(s, M, Kc);
 }
 
-__device__ inline bool final_update(Slab &s, GaussState &g, int N, const Scratch &sc)
+__device__ inline bool final_update(Slab &s, GaussState &g, int N, const Scratch &sc, bool keep_H)
 {   // FinalUpdate*: H = beta PHI'PHI + diag(alpha), SIGMA = H^-1, Mu  (MainEff.c:1841-1921)
     // PHI'PHI is not recomputed (the reference's dgemm, :1869-1874): it is kept up to date by the add and delete
     // actions -- a new column's products with the active columns are entries of the cache row the add has just
@@ -1333,7 +1347,8 @@ __device__ inline bool final_update(Slab &s, GaussState &g, int N, const Scratch
         for (int i = threadIdx.x & 31; i < M; i += 32) {
             double v = s.ptp[(size_t)j * cap + i] * beta;
             if (i == j) v += s.alpha[i];
-            s.H[j * M + i] = v; s.sigma[j * M + i] = v;
+            if (keep_H) s.H[j * M + i] = v;       // read by the Wald score of a full-model dump only (:206-215): a CV fit never writes it
+            s.sigma[j * M + i] = v;
         }
     __syncthreads();
     const bool ok = spd_inverse_sweep(s.sigma, M, s.colk, sc, sc.sweep);
@@ -1603,12 +1618,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                             }
                             if (threadIdx.x == 0) s.ptp[(size_t)M * cap + M] = s.G[(size_t)grow_new * Kc + nu];
                             __syncthreads();
-                            for (int i = threadIdx.x; i < M; i += T) {       // SIGMA is symmetric: walk column i so that a warp's loads coalesce
-                                double z = 0;
-#pragma unroll 4
-                                for (int j = 0; j < M; j++) z = fma(s.sigma[j * M + i], s.tmp[j], z);
-                                s.u[i] = z;
-                            }
+                            for (int i = threadIdx.x; i < M; i += T) s.u[i] = sym_matvec_row(s.sigma, M, i, s.tmp);
                             for (int h = threadIdx.x; h < LD; h += T) s.phi[(size_t)M * LD + h] = h < N ? s.phinew[h] : 0.0;
                             const double s_ii = 1.0 / (new_alpha + s.S_in[nu]);
                             const double mu_i = s_ii * s.Q_in[nu];
@@ -1750,7 +1760,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
                 g.beta = (N - sg) / ee;
                 if (g.beta > 1e6 / vt) g.beta = 1e6 / vt;
                 if (fabs(log(g.beta) - log(beta_old)) > 1e-6) {
-                    if (!final_update(s, g, N, sc)) g.status |= ST_NOT_PD;
+                    if (!final_update(s, g, N, sc, out.m_out != nullptr)) g.status |= ST_NOT_PD;
                     if (selected != ACT_TERM) full_stat(s, g, N, Kc, false, sc);
                 }
             }
@@ -1772,9 +1782,7 @@ __device__ void gauss_fit(const Problem &P, const FoldData &F, const Variant &v,
             __syncthreads();
             double q11 = 0, q1y = 0, sy = 0;
             for (int j = threadIdx.x; j < M; j += T) {
-                double z = 0;
-#pragma unroll 4
-                for (int k = 0; k < M; k++) z = fma(s.sigma[k * M + j], s.tmp[k], z);      // (symmetric: coalesced column walk)
+                const double z = sym_matvec_row(s.sigma, M, j, s.tmp);
                 q11 = fma(z, s.tmp[j], q11); q1y = fma(z, s.u[j], q1y);
             }
             block_sum2(q11, q1y, sc);
