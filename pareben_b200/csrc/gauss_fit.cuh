@@ -864,16 +864,17 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
             for (int q = 0; q < 8; q++) {
                 if (q < NBp) {
                     const int j = k0 + q;
-                    Pn[q * Mp + i] = (q < nb && i < M) ? (i >= j ? a[(size_t)j * M + i] : a[(size_t)i * M + j]) : 0.0;
-                    C[q * Mp + i] = 0.0;                  // rows past nb and entries past M contribute nothing to the update
+                    const double v = (q < nb && i < M) ? (i >= j ? a[(size_t)j * M + i] : a[(size_t)i * M + j]) : 0.0;
+                    Pn[q * Mp + i] = v;
+                    C[q * Mp + i] = q == 0 ? v : 0.0;     // C_0 = the first pivot's column; rows past nb and entries past M contribute nothing to the update
                 }
             }
         }
         if (threadIdx.x < NBp) dv[threadIdx.x] = 0.0;
         // phase A: the pivots of this panel, applied to the panel's own columns
+        // (C_p, the pivot's pre-update column that phase B needs, is written by the warp that updates column p during pivot
+        //  p - 1 -- C_0 by the load above -- so a pivot costs one barrier)
         for (int p = 0; p < nb; p++) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < M; i += T) C[p * Mp + i] = Pn[p * Mp + i];
             __syncthreads();
             const int k = k0 + p;
             const double *cp = C + p * Mp;
@@ -884,6 +885,7 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
             for (int q = wid; q < nb; q += nw) {              // a warp per panel column, lanes over rows (no integer division)
                 const int j = k0 + q;
                 const double cj = cp[j];
+                const bool next_pivot = q == p + 1;
                 for (int i = lane; i < M; i += 32) {
                     double v;
                     if (i == k && j == k) v = -dinv;
@@ -891,6 +893,7 @@ __device__ inline bool sweep_panel(double *a, int M, double *sm)
                     else if (j == k) v = cp[i] * dinv;
                     else v = Pn[q * Mp + i] - (cp[i] * cj) * dinv;
                     Pn[q * Mp + i] = v;
+                    if (next_pivot) C[q * Mp + i] = v;
                 }
             }
         }
