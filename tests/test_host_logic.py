@@ -143,3 +143,39 @@ def test_two_rank_gloo_merge(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_gram_organisation_identities(bundled):
+    """What the Gram organisation of the Gaussian kernels rests on, checked in numpy on the bundled design:
+    (i) the candidate-cache row of basis p, sum_h (x_c[h]/s_c)(x_p[h]/s_p) as CacheBP* computes it
+    (elasticNetLinearNeMainEff.c:1157-1178), is row p of one matrix per fold -- it involves neither the response nor any
+    solver state; for genotype codes the dot products are exact integers, so the shared matrix differs from the reference's
+    per-term-rounded sum by a few ulp;
+    (ii) ||t - PHI mu||^2 = t't - 2 mu'(PHI't) + mu'(PHI'PHI)mu with PHI't = xt[used] and PHI'PHI = C[used][:, used], to
+    1e-13 relative when the residual is 1 % of t't (where the outer loop stops)."""
+    import pareben_b200 as pb
+    X = bundled["BASIS"].astype(np.float64)
+    y = bundled["y"].astype(np.float64)
+    folds = pb.AssignToFolds(X, 10)
+    tr = folds != 1
+    Xf, t = X[tr], y[tr] - y[tr].mean()
+    s = np.sqrt((Xf * Xf).sum(axis=0)); s[s == 0] = 1.0
+    ints = Xf.T @ Xf
+    assert np.array_equal(ints, np.rint(ints))                      # exact integer dot products
+    C = ints / np.outer(s, s)
+    Z = Xf / s                                                      # the reference normalises BASIS in place (:87-99)
+    used = np.array([0, 17, 230, 480, 5, 99])
+    for p in used:
+        row = np.array([np.dot(Z[:, c], Z[:, p]) for c in range(X.shape[1])])      # CacheBP*'s loop
+        assert np.max(np.abs(row - C[p])) < 1e-14                   # correlations, |.| <= 1: a few ulp (an exact 0 in C is 5e-18 there)
+    # (ii): a posterior mean that leaves 1 % of the variance -- fit on a response the six columns explain almost fully
+    PHI = Z[:, used]
+    rng = np.random.default_rng(3)
+    t2 = PHI @ rng.normal(0, 1, used.size); t2 += 0.1 * np.linalg.norm(t2) / np.sqrt(t2.size) * rng.normal(0, 1, t2.size)
+    mu = np.linalg.lstsq(PHI, t2, rcond=None)[0]
+    direct = np.sum((t2 - PHI @ mu) ** 2)
+    xt = Z.T @ t2
+    gram = t2 @ t2 - 2 * mu @ xt[used] + mu @ C[np.ix_(used, used)] @ mu
+    assert direct / (t2 @ t2) < 0.02
+    assert abs(gram - direct) / direct < 1e-12
+    assert t.size == Xf.shape[0]
