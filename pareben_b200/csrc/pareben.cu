@@ -875,7 +875,14 @@ int run_fits_impl(pareben_problem *p, int n_fits, const int *fold, const double 
         P.N = p->n; P.K = p->k; P.Kc = p->kc; P.n_folds = p->n_folds; P.epis = p->epis; P.prior = p->prior;
         P.cap = p->cap; P.nmax = p->nmax; P.folds = p->d_folds;
         const Variant v = make_variant(p->epis, p->prior);
-        const int grid = std::min(p->n_slabs, n_fits);
+        int grid = std::min(p->n_slabs, n_fits);
+        // A launch with few fits per SM (one shard of a grid split over 8 GPUs: 250 fits for 148 SMs): a binomial fit that has
+        // an SM to itself -- all four tensor pipes, the whole L1 -- finishes sooner than two sharing it, and the launch is as long
+        // as its longest fits.  Measured (scripts/shard_blocks.py, config-2 shards): 200 / 250 / 286 / 334 fits 40.1 / 57.0 / 58.8 /
+        // 61.4 ms with two blocks per SM against 36.5 / 52.9 / 53.0 / 55.2 ms with one; from 400 fits on two blocks win (42.9
+        // against 49.5 ms), and the Gaussian kernel never gains.  The tables do not depend on the grid size.
+        if (p->prior == PAREBEN_BINOMIAL && !getenv("PAREBEN_BLOCKS_PER_SM") && n_fits > p->sm_count && (long long)n_fits * 10 <= (long long)p->sm_count * 23)
+            grid = std::min(grid, p->sm_count);
         CU(cudaEventRecord(p->ev0, p->stream));
         if (p->prior == PAREBEN_GAUSSIAN)
             CU((p->epis ? launch_fit_ge : launch_fit_gm)(grid, p->threads, p->stream, P, v, d_tasks, n_fits, sched, p->d_slabs, p->slab_stride, out));
